@@ -1,0 +1,185 @@
+/*
+ * gsplat_b200.h -- C ABI of libgsplat_b200.so: the B200 (sm_100a) implementation of the
+ * GaussianRenderer.render hot path of Loveof1ife7/mini-3d-gaussian-splatting.
+ *
+ * The reference has no FFI (it is pure Python/torch); each entry point below replaces one
+ * reference *method* and is what a binding for that method would call.  Citations are
+ * file:line into the reference tree.
+ *
+ *   gs_project_fwd / gs_project_bwd   GaussianRenderer._project_gaussians_3d_to_2d  src/core/renderer.py:117-200
+ *                                     + GaussianModel.compute_3d_covariance         src/core/gaussian_model.py:200-207
+ *                                     + MathUtils.build_rotation_matrix             src/utils/math_utils.py:9-26
+ *                                     + activations get_opacity / sigmoid(features) src/core/gaussian_model.py:120-122, renderer.py:88-94
+ *                                     + GaussianRenderer._frustum_culling           src/core/renderer.py:201-220
+ *   gs_bin_prepare / gs_bin_sort      GaussianRenderer._sort_gaussians_by_depth     src/core/renderer.py:222-239
+ *                                     + the tile-list building loop                 src/core/renderer.py:263-298
+ *   gs_raster_fwd / gs_raster_bwd     the pixel loop + epilogue of _tile_rasterization  src/core/renderer.py:300-367
+ *                                     (backward = what torch autograd derives from it)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates or frees device memory: outputs and scratch are caller-owned
+ *     (query gs_bin_workspace_bytes, then run);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - return value: 0 = ok, negative = GsStatus; text via gs_last_error_string() (thread-local);
+ *   - fp32 everywhere; row-major contiguous arrays unless a stride is given;
+ *   - re-entrant: no global mutable state.
+ */
+#ifndef GSPLAT_B200_H_
+#define GSPLAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 3
+
+typedef enum GsStatus {
+    GS_OK = 0,
+    GS_ERR_INVALID_ARGUMENT = -1,
+    GS_ERR_CUDA = -2,
+    GS_ERR_WORKSPACE_TOO_SMALL = -3,
+    GS_ERR_UNSUPPORTED = -4
+} GsStatus;
+
+/* Camera block, HOST memory, 16 floats:
+ *   [0..8]  Rv  row-major 3x3  = world_view_transform()[:3,:3]      renderer.py:150-151
+ *   [9..11] Tv                 = world_view_transform()[:3,3]       renderer.py:152
+ *   [12] fx = 0.5*W/tan(FoVx/2)  [13] fy = 0.5*H/tan(FoVy/2)  [14] cx = W/2  [15] cy = H/2   renderer.py:142-147
+ * (computed in double on the host and rounded once to fp32, as the reference does). */
+#define GS_CAMERA_FLOATS 16
+
+/* Per-splat record consumed by the raster kernels: 12 floats = 3 x float4, 48-byte stride.
+ *   {mx, my, Q00, Q01+Q10} {Q11, opacity, depth, r} {g, b, 0, 0} */
+#define GS_SPLAT_REC_FLOATS 12
+
+int gs_abi_version(void);
+const char* gs_last_error_string(void);
+/* Compute capability the kernels were built for (100 for sm_100a). */
+int gs_built_for_sm(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage P+M+C: projection, fused with activations, 3-D covariance and frustum culling.
+ *
+ * Two input modes, mirroring the two ways the reference renderer is fed:
+ *   parameter mode  (scaling_log != NULL && rotation != NULL): raw GaussianModel parameters;
+ *        Sigma = R(normalize(rotation)) diag(exp(scaling_log)^2) R^T is formed in registers.
+ *   covariance mode (cov3d != NULL): a ready [n,3,3] covariance, as the duck-typed
+ *        `gaussians.get_covariance` of the reference's own tests (tests/test_renderer.py:48-53).
+ * opacity: [n]; a logit when opacity_is_logit != 0 (sigmoid is fused), else already activated.
+ * feat0:   pointer to features[0,0,0]; row i, channel c is feat0[i*feat_stride + c]; the colour
+ *          is sigmoid(features[:,0,:]) (renderer.py:88-92).
+ *
+ * Outputs (all length n, invisible splats included -- renderer.py:106-114):
+ *   means2d [n,2]  depths [n]  conics [n,2,2]  radii [n] (float)  colors [n,3]  opacities [n]
+ *   vis [n] (0/1 bytes = visibility_filter)
+ *   tiles_touched [n] int32: tiles of the splat's integer AABB (0 if culled or empty)   renderer.py:278-293
+ *   tile_rect [n,4] uint16: tx0, ty0, tx1, ty1 inclusive (valid when tiles_touched > 0)
+ *   depth_keys [n] uint32: fp32 bits of depth for splats with tiles_touched > 0; 0xFFFFFFFE for visible
+ *                          splats whose AABB is empty; 0xFFFFFFFF for culled splats
+ *   splat_rec [n,12]: packed copy for the raster kernels (GS_SPLAT_REC_FLOATS)
+ * ------------------------------------------------------------------------------------- */
+int gs_project_fwd(int64_t n,
+                   const float* xyz,
+                   const float* scaling_log, const float* rotation,
+                   const float* cov3d,
+                   const float* opacity, int32_t opacity_is_logit,
+                   const float* feat0, int64_t feat_stride,
+                   const float* camera_host,
+                   int32_t img_w, int32_t img_h, int32_t tile_size,
+                   float radius_min, float radius_max,
+                   float* means2d, float* depths, float* conics, float* radii,
+                   float* colors, float* opacities, uint8_t* vis,
+                   int32_t* tiles_touched, uint16_t* tile_rect, uint32_t* depth_keys,
+                   float* splat_rec,
+                   void* stream);
+
+/* Backward of gs_project_fwd.  Upstream gradients: g_means2d [n,2], g_conics [n,2,2],
+ * g_depths [n], g_colors [n,3], g_opacities [n].  Results are WRITTEN (not accumulated):
+ *   g_xyz [n,3]; parameter mode: g_scaling_log [n,3], g_rotation [n,4]; covariance mode: g_cov3d [n,3,3];
+ *   g_opacity [n] (w.r.t. the logit when opacity_is_logit, else w.r.t. the activated value);
+ *   g_feat0: row i channel c at g_feat0[i*g_feat_stride + c]; other feature rows are the
+ *            caller's to zero (the reference yields zeros there -- SURVEY 3.2). */
+int gs_project_bwd(int64_t n,
+                   const float* xyz,
+                   const float* scaling_log, const float* rotation,
+                   const float* cov3d,
+                   const float* opacity, int32_t opacity_is_logit,
+                   const float* feat0, int64_t feat_stride,
+                   const float* camera_host,
+                   const float* g_means2d, const float* g_conics, const float* g_depths,
+                   const float* g_colors, const float* g_opacities,
+                   float* g_xyz, float* g_scaling_log, float* g_rotation, float* g_cov3d,
+                   float* g_opacity, float* g_feat0, int64_t g_feat_stride,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage S+B: global depth order and per-tile lists.
+ *
+ * The reference sorts visible splats by depth once and appends each, in that order, to the
+ * list of every tile its AABB touches.  That is the sequence obtained by a stable sort of
+ * (tile_id << 32 | depth_bits) keys emitted in ascending splat index; it is produced here as
+ *   gs_bin_prepare: stable radix sort of depth_keys (ties -> ascending index), gather of
+ *                   tiles_touched in that order, exclusive prefix sum;
+ *                   counters[0] = splats with >= 1 tile, counters[1] = D (tile pairs),
+ *                   counters[2] = splats that passed culling (3 x int64)
+ *   -- caller reads the counters back (the one host sync of the frame) --
+ *   gs_bin_sort:    duplication in depth order, stable radix sort on the tile id alone,
+ *                   tile-range extraction.
+ * Outputs: entry_ids [D] int32 splat ids grouped by tile, front to back;
+ *          tile_ranges [num_tiles,2] int32 = [begin,end) into entry_ids;
+ *          entry_keys [D] uint64 (optional, may be NULL) = tile_id<<32 | depth_bits of each entry,
+ *          for parity checks against the reference order.
+ * ------------------------------------------------------------------------------------- */
+int64_t gs_bin_workspace_bytes(int64_t n, int64_t d_capacity, int32_t num_tiles);
+
+int gs_bin_prepare(int64_t n,
+                   const uint32_t* depth_keys, const int32_t* tiles_touched,
+                   void* workspace, int64_t workspace_bytes,
+                   int32_t* sorted_ids, int64_t* offsets, int64_t* counters,
+                   void* stream);
+
+int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
+                const int32_t* sorted_ids, const int64_t* offsets,
+                const uint16_t* tile_rect, const uint32_t* depth_keys,
+                int32_t tiles_x, int32_t num_tiles,
+                void* workspace, int64_t workspace_bytes,
+                int32_t* entry_ids, int32_t* tile_ranges, uint64_t* entry_keys,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage R: 16x16-tile front-to-back compositing.
+ *
+ * bg: 3 floats (device).  `any_visible_host` (= counters[2] > 0) says whether any splat passed
+ * culling: the reference returns the background ONCE, unclamped, when nothing is visible
+ * (renderer.py:74-83) and adds it TWICE otherwise (renderer.py:273 + :359).
+ * Outputs: image [3,H,W], alpha [1,H,W], depth [1,H,W];
+ *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue,
+ *   n_consumed [H*W] int32 = list entries the pixel walked, tile_consumed [num_tiles] int32 = max of it.
+ * ------------------------------------------------------------------------------------- */
+int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
+                  const int32_t* entry_ids, const int32_t* tile_ranges,
+                  const float* splat_rec, const float* bg, int32_t any_visible_host,
+                  float* image, float* alpha, float* depth,
+                  float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
+                  void* stream);
+
+/* Backward of gs_raster_fwd.  g_image [3,H,W], g_alpha [1,H,W], g_depth [1,H,W] upstream.
+ * Gradients are ACCUMULATED (atomic adds) into caller-zeroed g_means2d [n,2], g_conics [n,2,2],
+ * g_depths [n], g_colors [n,3], g_opacities [n]. */
+int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
+                  const int32_t* entry_ids, const int32_t* tile_ranges,
+                  const float* splat_rec, const float* bg,
+                  const float* alpha, const float* pix_state,
+                  const int32_t* n_consumed, const int32_t* tile_consumed,
+                  const float* g_image, const float* g_alpha, const float* g_depth,
+                  float* g_means2d, float* g_conics, float* g_depths,
+                  float* g_colors, float* g_opacities,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H_ */

@@ -1,0 +1,462 @@
+// Stage P+M+C: fused activation + 3-D covariance + EWA projection + conic + radius + culling
+// + tile rectangle, forward and backward.  One thread per Gaussian; the work is a pure stream
+// over the parameter SoA (HBM-bound, no reuse), so the kernels are sized for coalescing and
+// many loads in flight rather than for shared-memory staging.
+//
+// Reference semantics: src/core/renderer.py:117-220, src/core/gaussian_model.py:200-207,
+// src/utils/math_utils.py:9-26.
+#include "common.cuh"
+
+namespace gs {
+
+struct Splat3D {
+    float S[9];   // 3-D covariance, row-major (general 3x3: the covariance-mode input may be any matrix)
+    // parameter mode only:
+    float R[9];   // rotation matrix
+    float sig[3]; // exp(scaling_log)
+    float qh[4];  // normalised quaternion (w,x,y,z)
+    float qn;     // max(|rotation|, 1e-12)
+};
+
+struct Proj {
+    float X, Y, Z, iz;
+    float mx, my;
+    float J00, J02, J11, J12;
+    float M[9];     // Rv S Rv^T
+    float a, b01, b10, c;   // cov2d (+1e-6 on the diagonal)
+    float det;
+    float q00, q01, q10, q11;
+    float radius;
+};
+
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+}
+__device__ __forceinline__ void mat3_mul_bt(const float* A, const float* B, float* C) {  // A * B^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[j * 3 + 0] + A[i * 3 + 1] * B[j * 3 + 1] + A[i * 3 + 2] * B[j * 3 + 2];
+}
+__device__ __forceinline__ void mat3_mul_at(const float* A, const float* B, float* C) {  // A^T * B
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[0 * 3 + i] * B[0 * 3 + j] + A[1 * 3 + i] * B[1 * 3 + j] + A[2 * 3 + i] * B[2 * 3 + j];
+}
+
+// gaussian_model.py:113-118,200-207 + math_utils.py:9-26
+__device__ __forceinline__ void covariance_from_params(const float* __restrict__ scaling_log,
+                                                       const float* __restrict__ rotation,
+                                                       int64_t i, Splat3D& g) {
+    const float s0 = scaling_log[i * 3 + 0], s1 = scaling_log[i * 3 + 1], s2 = scaling_log[i * 3 + 2];
+    const float4 q = *reinterpret_cast<const float4*>(rotation + i * 4);
+    g.sig[0] = expf(s0);
+    g.sig[1] = expf(s1);
+    g.sig[2] = expf(s2);
+    // F.normalize: q / max(|q|, 1e-12); the reference applies it twice (get_rotation, then
+    // build_rotation_matrix); the second pass only matters at rounding level but is kept.
+    float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    n = fmaxf(n, 1e-12f);
+    g.qn = n;
+    float w = q.x / n, x = q.y / n, y = q.z / n, z = q.w / n;
+    float n2 = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-12f);
+    w /= n2; x /= n2; y /= n2; z /= n2;
+    g.qh[0] = w; g.qh[1] = x; g.qh[2] = y; g.qh[3] = z;
+    const float xx = x * x, yy = y * y, zz = z * z;
+    const float wx = w * x, wy = w * y, wz = w * z;
+    const float xy = x * y, xz = x * z, yz = y * z;
+    g.R[0] = 1.f - 2.f * (yy + zz); g.R[1] = 2.f * (xy - wz);       g.R[2] = 2.f * (xz + wy);
+    g.R[3] = 2.f * (xy + wz);       g.R[4] = 1.f - 2.f * (xx + zz); g.R[5] = 2.f * (yz - wx);
+    g.R[6] = 2.f * (xz - wy);       g.R[7] = 2.f * (yz + wx);       g.R[8] = 1.f - 2.f * (xx + yy);
+    const float d0 = g.sig[0] * g.sig[0], d1 = g.sig[1] * g.sig[1], d2 = g.sig[2] * g.sig[2];
+    // Sigma = R diag(d) R^T (symmetric by construction)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = r; c < 3; ++c) {
+            const float v = g.R[r * 3 + 0] * d0 * g.R[c * 3 + 0] + g.R[r * 3 + 1] * d1 * g.R[c * 3 + 1] +
+                            g.R[r * 3 + 2] * d2 * g.R[c * 3 + 2];
+            g.S[r * 3 + c] = v;
+            g.S[c * 3 + r] = v;
+        }
+}
+
+// renderer.py:154-192.  The sub-expressions that feed integer casts and the culling compares
+// (camera-space position, pixel centre) reproduce the reference's rounding exactly:
+// MKL evaluates `Xw @ Rv.T` as x0*r0 followed by two FMAs, `+ Tv` is a separate add, and
+// `fx * X / Z + cx` is three separately rounded ops.
+__device__ __forceinline__ void project_point(const Camera& cam, float x0, float x1, float x2,
+                                              const float* S, float rmin, float rmax, Proj& p) {
+    p.X = add_rn(__fmaf_rn(x2, cam.r[2], __fmaf_rn(x1, cam.r[1], mul_rn(x0, cam.r[0]))), cam.t[0]);
+    p.Y = add_rn(__fmaf_rn(x2, cam.r[5], __fmaf_rn(x1, cam.r[4], mul_rn(x0, cam.r[3]))), cam.t[1]);
+    p.Z = add_rn(__fmaf_rn(x2, cam.r[8], __fmaf_rn(x1, cam.r[7], mul_rn(x0, cam.r[6]))), cam.t[2]);
+    p.mx = add_rn(div_rn(mul_rn(cam.fx, p.X), p.Z), cam.cx);
+    p.my = add_rn(div_rn(mul_rn(-cam.fy, p.Y), p.Z), cam.cy);
+
+    float tmp[9];
+    mat3_mul(cam.r, S, tmp);          // Rv S
+    mat3_mul_bt(tmp, cam.r, p.M);     // (Rv S) Rv^T
+    p.iz = div_rn(1.0f, p.Z);
+    p.J00 = cam.fx * p.iz;
+    p.J02 = -cam.fx * p.X * p.iz * p.iz;
+    p.J11 = -cam.fy * p.iz;
+    p.J12 = cam.fy * p.Y * p.iz * p.iz;
+    // cov2d = J M J^T + 1e-6 I with J = [[J00,0,J02],[0,J11,J12]]
+    const float* M = p.M;
+    const float u0 = p.J00 * M[0] + p.J02 * M[6];   // (J M) row 0
+    const float u1 = p.J00 * M[1] + p.J02 * M[7];
+    const float u2 = p.J00 * M[2] + p.J02 * M[8];
+    const float v0 = p.J11 * M[3] + p.J12 * M[6];   // row 1
+    const float v1 = p.J11 * M[4] + p.J12 * M[7];
+    const float v2 = p.J11 * M[5] + p.J12 * M[8];
+    p.a = (u0 * p.J00 + u2 * p.J02) + 1e-6f;
+    p.b01 = u1 * p.J11 + u2 * p.J12;
+    p.b10 = v0 * p.J00 + v2 * p.J02;
+    p.c = (v1 * p.J11 + v2 * p.J12) + 1e-6f;
+    p.det = p.a * p.c - p.b01 * p.b10;
+    const float id = 1.0f / p.det;
+    p.q00 = p.c * id;
+    p.q01 = -p.b01 * id;
+    p.q10 = -p.b10 * id;
+    p.q11 = p.a * id;
+    // lambda_max of the symmetric matrix eigvalsh sees (lower triangle): SURVEY 8c closed form
+    const float mid = 0.5f * (p.a + p.c);
+    const float hd = 0.5f * (p.a - p.c);
+    const float lam = mid + sqrtf(hd * hd + p.b10 * p.b10);
+    const float r = 3.0f * sqrtf(lam);
+    // torch.clamp propagates NaN; fminf/fmaxf would swallow it
+    p.radius = (r != r) ? r : fminf(fmaxf(r, rmin), rmax);
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <bool kParamMode>
+__global__ void __launch_bounds__(256)
+project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __restrict__ scaling_log,
+                   const float* __restrict__ rotation, const float* __restrict__ cov3d,
+                   const float* __restrict__ opacity, int opacity_is_logit,
+                   const float* __restrict__ feat0, int64_t feat_stride, Camera cam,
+                   int img_w, int img_h, int tiles_x_unused, float rmin, float rmax,
+                   float2* __restrict__ means2d, float* __restrict__ depths, float4* __restrict__ conics,
+                   float* __restrict__ radii, float* __restrict__ colors, float* __restrict__ opac_out,
+                   uint8_t* __restrict__ vis_out, int32_t* __restrict__ tiles_touched,
+                   ushort4* __restrict__ tile_rect, uint32_t* __restrict__ depth_keys,
+                   float4* __restrict__ rec) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+
+    Splat3D g;
+    if (kParamMode) {
+        covariance_from_params(scaling_log, rotation, i, g);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g.S[k] = cov3d[i * 9 + k];
+    }
+    const float x0 = xyz[i * 3 + 0], x1 = xyz[i * 3 + 1], x2 = xyz[i * 3 + 2];
+    Proj p;
+    project_point(cam, x0, x1, x2, g.S, rmin, rmax, p);
+
+    const float op_in = opacity[i];
+    const float op = opacity_is_logit ? sigmoidf(op_in) : op_in;
+    const float cr = sigmoidf(feat0[i * feat_stride + 0]);
+    const float cg = sigmoidf(feat0[i * feat_stride + 1]);
+    const float cb = sigmoidf(feat0[i * feat_stride + 2]);
+
+    // renderer.py:218 -- every compare is false for NaN, exactly as in torch
+    const float r = p.radius;
+    const float Wf = (float)img_w, Hf = (float)img_h;
+    const bool vis = (p.Z > 0.f) && (p.mx >= -r) && (p.mx < add_rn(Wf, r)) && (p.my >= -r) &&
+                     (p.my < add_rn(Hf, r)) && (r > 0.f);
+
+    // renderer.py:278-293 (Python int() == C truncation toward zero)
+    int cnt = 0;
+    ushort4 rect = make_ushort4(0, 0, 0, 0);
+    if (vis) {
+        const int ir = (int)r, ix = (int)p.mx, iy = (int)p.my;
+        const int px0 = max(ix - ir, 0), px1 = min(ix + 1 + ir, img_w);
+        const int py0 = max(iy - ir, 0), py1 = min(iy + 1 + ir, img_h);
+        if (px0 < px1 && py0 < py1) {
+            const int tx0 = px0 / kTile, tx1 = (px1 - 1) / kTile;
+            const int ty0 = py0 / kTile, ty1 = (py1 - 1) / kTile;
+            cnt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+            rect = make_ushort4((unsigned short)tx0, (unsigned short)ty0, (unsigned short)tx1, (unsigned short)ty1);
+        }
+    }
+
+    means2d[i] = make_float2(p.mx, p.my);
+    depths[i] = p.Z;
+    conics[i] = make_float4(p.q00, p.q01, p.q10, p.q11);
+    radii[i] = r;
+    colors[i * 3 + 0] = cr;
+    colors[i * 3 + 1] = cg;
+    colors[i * 3 + 2] = cb;
+    opac_out[i] = op;
+    vis_out[i] = vis ? 1 : 0;
+    tiles_touched[i] = cnt;
+    tile_rect[i] = rect;
+    // valid depths are < 0x7F800001, so the two sentinels sort behind every binned splat
+    depth_keys[i] = cnt > 0 ? __float_as_uint(p.Z) : (vis ? 0xFFFFFFFEu : 0xFFFFFFFFu);
+    rec[i * 3 + 0] = make_float4(p.mx, p.my, p.q00, add_rn(p.q01, p.q10));
+    rec[i * 3 + 1] = make_float4(p.q11, op, p.Z, cr);
+    rec[i * 3 + 2] = make_float4(cg, cb, 0.f, 0.f);
+}
+
+// Backward (derived from the forward above).
+template <bool kParamMode>
+__global__ void __launch_bounds__(256)
+project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __restrict__ scaling_log,
+                   const float* __restrict__ rotation, const float* __restrict__ cov3d,
+                   const float* __restrict__ opacity, int opacity_is_logit,
+                   const float* __restrict__ feat0, int64_t feat_stride, Camera cam,
+                   const float2* __restrict__ g_means2d, const float4* __restrict__ g_conics,
+                   const float* __restrict__ g_depths, const float* __restrict__ g_colors,
+                   const float* __restrict__ g_opac,
+                   float* __restrict__ g_xyz, float* __restrict__ g_scaling, float4* __restrict__ g_rotation,
+                   float* __restrict__ g_cov3d, float* __restrict__ g_opacity,
+                   float* __restrict__ g_feat0, int64_t g_feat_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+
+    const float2 gm = g_means2d[i];
+    const float4 gq = g_conics[i];
+    const float gz_in = g_depths[i];
+    const float gcr = g_colors[i * 3 + 0], gcg = g_colors[i * 3 + 1], gcb = g_colors[i * 3 + 2];
+    const float gop = g_opac[i];
+
+    // activations
+    {
+        const float op_in = opacity[i];
+        float go = gop;
+        if (opacity_is_logit) {
+            const float o = sigmoidf(op_in);
+            go = gop * o * (1.f - o);
+        }
+        g_opacity[i] = go;
+        const float cr = sigmoidf(feat0[i * feat_stride + 0]);
+        const float cg = sigmoidf(feat0[i * feat_stride + 1]);
+        const float cb = sigmoidf(feat0[i * feat_stride + 2]);
+        g_feat0[i * g_feat_stride + 0] = gcr * cr * (1.f - cr);
+        g_feat0[i * g_feat_stride + 1] = gcg * cg * (1.f - cg);
+        g_feat0[i * g_feat_stride + 2] = gcb * cb * (1.f - cb);
+    }
+
+    const bool any_geo = (gm.x != 0.f) || (gm.y != 0.f) || (gq.x != 0.f) || (gq.y != 0.f) || (gq.z != 0.f) ||
+                         (gq.w != 0.f) || (gz_in != 0.f);
+    if (!any_geo) {
+        // nothing reached this splat through the rasteriser: all geometric gradients are zero
+        g_xyz[i * 3 + 0] = 0.f; g_xyz[i * 3 + 1] = 0.f; g_xyz[i * 3 + 2] = 0.f;
+        if (kParamMode) {
+            g_scaling[i * 3 + 0] = 0.f; g_scaling[i * 3 + 1] = 0.f; g_scaling[i * 3 + 2] = 0.f;
+            g_rotation[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g_cov3d[i * 9 + k] = 0.f;
+        }
+        return;
+    }
+
+    Splat3D g;
+    if (kParamMode) {
+        covariance_from_params(scaling_log, rotation, i, g);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g.S[k] = cov3d[i * 9 + k];
+    }
+    const float x0 = xyz[i * 3 + 0], x1 = xyz[i * 3 + 1], x2 = xyz[i * 3 + 2];
+    Proj p;
+    project_point(cam, x0, x1, x2, g.S, 0.f, 1e30f, p);
+
+    // conic = inv(cov2d):  g_cov2d = -Q^T gQ Q^T
+    float G2[4];
+    {
+        const float Q[4] = {p.q00, p.q01, p.q10, p.q11};
+        const float gQ[4] = {gq.x, gq.y, gq.z, gq.w};
+        // T = Q^T gQ
+        const float t00 = Q[0] * gQ[0] + Q[2] * gQ[2];
+        const float t01 = Q[0] * gQ[1] + Q[2] * gQ[3];
+        const float t10 = Q[1] * gQ[0] + Q[3] * gQ[2];
+        const float t11 = Q[1] * gQ[1] + Q[3] * gQ[3];
+        // G2 = -(T Q^T)
+        G2[0] = -(t00 * Q[0] + t01 * Q[1]);
+        G2[1] = -(t00 * Q[2] + t01 * Q[3]);
+        G2[2] = -(t10 * Q[0] + t11 * Q[1]);
+        G2[3] = -(t10 * Q[2] + t11 * Q[3]);
+    }
+    const float J[6] = {p.J00, 0.f, p.J02, 0.f, p.J11, p.J12};
+    // gM = J^T G2 J   (3x3)
+    float gM[9];
+    {
+        float GJ[6];  // G2 J (2x3)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            GJ[c] = G2[0] * J[c] + G2[1] * J[3 + c];
+            GJ[3 + c] = G2[2] * J[c] + G2[3] * J[3 + c];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gM[r * 3 + c] = J[r] * GJ[c] + J[3 + r] * GJ[3 + c];
+    }
+    // gJ = G2 J M^T + G2^T J M   (2x3)
+    float gJ[6];
+    {
+        float JMt[6], JM[6];
+        const float* M = p.M;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                JMt[r * 3 + c] = J[r * 3 + 0] * M[c * 3 + 0] + J[r * 3 + 1] * M[c * 3 + 1] + J[r * 3 + 2] * M[c * 3 + 2];
+                JM[r * 3 + c] = J[r * 3 + 0] * M[0 * 3 + c] + J[r * 3 + 1] * M[1 * 3 + c] + J[r * 3 + 2] * M[2 * 3 + c];
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            gJ[c] = G2[0] * JMt[c] + G2[1] * JMt[3 + c] + G2[0] * JM[c] + G2[2] * JM[3 + c];
+            gJ[3 + c] = G2[2] * JMt[c] + G2[3] * JMt[3 + c] + G2[1] * JM[c] + G2[3] * JM[3 + c];
+        }
+    }
+    const float iz = p.iz, iz2 = iz * iz, iz3 = iz2 * iz;
+    const float fx = cam.fx, fy = cam.fy;
+    const float gX = gm.x * fx * iz + gJ[2] * (-fx * iz2);
+    const float gY = gm.y * (-fy * iz) + gJ[5] * (fy * iz2);
+    const float gZ = gz_in + gm.x * (-fx * p.X * iz2) + gm.y * (fy * p.Y * iz2) + gJ[0] * (-fx * iz2) +
+                     gJ[2] * (2.f * fx * p.X * iz3) + gJ[4] * (fy * iz2) + gJ[5] * (-2.f * fy * p.Y * iz3);
+    g_xyz[i * 3 + 0] = cam.r[0] * gX + cam.r[3] * gY + cam.r[6] * gZ;
+    g_xyz[i * 3 + 1] = cam.r[1] * gX + cam.r[4] * gY + cam.r[7] * gZ;
+    g_xyz[i * 3 + 2] = cam.r[2] * gX + cam.r[5] * gY + cam.r[8] * gZ;
+
+    // gSigma = Rv^T gM Rv
+    float gS[9];
+    {
+        float tmp[9];
+        mat3_mul_at(cam.r, gM, tmp);
+        mat3_mul(tmp, cam.r, gS);
+    }
+    if (!kParamMode) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g_cov3d[i * 9 + k] = gS[k];
+        return;
+    }
+    // Sigma = R D R^T, D = diag(sig^2)
+    const float* R = g.R;
+    float gsym[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gsym[r * 3 + c] = gS[r * 3 + c] + gS[c * 3 + r];
+    float gR[9];
+    {
+        float tmp[9];
+        mat3_mul(gsym, R, tmp);   // (gS + gS^T) R
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gR[r * 3 + c] = tmp[r * 3 + c] * g.sig[c] * g.sig[c];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // (R^T gS R)_kk
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc += R[r * 3 + k] * gS[r * 3 + c] * R[c * 3 + k];
+        // d(sig^2)/d(log-scale) = 2 sig^2
+        g_scaling[i * 3 + k] = 2.f * acc * g.sig[k] * g.sig[k];
+    }
+    const float w = g.qh[0], x = g.qh[1], y = g.qh[2], z = g.qh[3];
+    const float gw = 2.f * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]);
+    const float gx = 2.f * (y * gR[1] + z * gR[2] + y * gR[3] - 2.f * x * gR[4] - w * gR[5] + z * gR[6] + w * gR[7] - 2.f * x * gR[8]);
+    const float gy = 2.f * (-2.f * y * gR[0] + x * gR[1] + w * gR[2] + x * gR[3] + z * gR[5] - w * gR[6] + z * gR[7] - 2.f * y * gR[8]);
+    const float gzq = 2.f * (-2.f * z * gR[0] - w * gR[1] + x * gR[2] + w * gR[3] - 2.f * z * gR[4] + y * gR[5] + x * gR[6] + y * gR[7]);
+    const float dotp = w * gw + x * gx + y * gy + z * gzq;
+    const float inv = 1.0f / g.qn;
+    g_rotation[i] = make_float4((gw - w * dotp) * inv, (gx - x * dotp) * inv, (gy - y * dotp) * inv, (gzq - z * dotp) * inv);
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_log, const float* rotation,
+                              const float* cov3d, const float* opacity, int32_t opacity_is_logit,
+                              const float* feat0, int64_t feat_stride, const float* camera_host,
+                              int32_t img_w, int32_t img_h, int32_t tile_size, float radius_min, float radius_max,
+                              float* means2d, float* depths, float* conics, float* radii, float* colors,
+                              float* opacities, uint8_t* vis, int32_t* tiles_touched, uint16_t* tile_rect,
+                              uint32_t* depth_keys, float* splat_rec, void* stream) {
+    GS_REQUIRE(n >= 0, "n < 0");
+    GS_REQUIRE(camera_host != nullptr, "camera_host is NULL");
+    GS_REQUIRE(img_w > 0 && img_h > 0, "image size must be positive");
+    if (tile_size != kTile) {
+        set_error("gs_project_fwd: tile_size %d unsupported (kernels are built for %d)", tile_size, kTile);
+        return GS_ERR_UNSUPPORTED;
+    }
+    GS_REQUIRE((img_w + kTile - 1) / kTile <= 65535 && (img_h + kTile - 1) / kTile <= 65535, "image too large for uint16 tile rects");
+    const bool param_mode = scaling_log != nullptr && rotation != nullptr;
+    GS_REQUIRE(param_mode || cov3d != nullptr, "need (scaling_log, rotation) or cov3d");
+    if (n == 0) return GS_OK;
+    GS_REQUIRE(xyz && opacity && feat0 && means2d && depths && conics && radii && colors && opacities && vis &&
+                   tiles_touched && tile_rect && depth_keys && splat_rec, "NULL array argument");
+    DeviceGuard guard(xyz);
+    const Camera cam = camera_from_host(camera_host);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (param_mode) {
+        project_fwd_kernel<true><<<blocks, threads, 0, st>>>(
+            n, xyz, scaling_log, rotation, nullptr, opacity, opacity_is_logit, feat0, feat_stride, cam, img_w, img_h, 0,
+            radius_min, radius_max, (float2*)means2d, depths, (float4*)conics, radii, colors, opacities, vis,
+            tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec);
+    } else {
+        project_fwd_kernel<false><<<blocks, threads, 0, st>>>(
+            n, xyz, nullptr, nullptr, cov3d, opacity, opacity_is_logit, feat0, feat_stride, cam, img_w, img_h, 0,
+            radius_min, radius_max, (float2*)means2d, depths, (float4*)conics, radii, colors, opacities, vis,
+            tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec);
+    }
+    GS_CUDA_TRY(cudaGetLastError());
+    return GS_OK;
+}
+
+extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_log, const float* rotation,
+                              const float* cov3d, const float* opacity, int32_t opacity_is_logit,
+                              const float* feat0, int64_t feat_stride, const float* camera_host,
+                              const float* g_means2d, const float* g_conics, const float* g_depths,
+                              const float* g_colors, const float* g_opacities, float* g_xyz, float* g_scaling_log,
+                              float* g_rotation, float* g_cov3d, float* g_opacity, float* g_feat0,
+                              int64_t g_feat_stride, void* stream) {
+    GS_REQUIRE(n >= 0, "n < 0");
+    GS_REQUIRE(camera_host != nullptr, "camera_host is NULL");
+    const bool param_mode = scaling_log != nullptr && rotation != nullptr;
+    GS_REQUIRE(param_mode || cov3d != nullptr, "need (scaling_log, rotation) or cov3d");
+    GS_REQUIRE(!param_mode || (g_scaling_log && g_rotation), "parameter mode needs g_scaling_log and g_rotation");
+    GS_REQUIRE(param_mode || g_cov3d, "covariance mode needs g_cov3d");
+    if (n == 0) return GS_OK;
+    GS_REQUIRE(xyz && opacity && feat0 && g_means2d && g_conics && g_depths && g_colors && g_opacities && g_xyz &&
+                   g_opacity && g_feat0, "NULL array argument");
+    DeviceGuard guard(xyz);
+    const Camera cam = camera_from_host(camera_host);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (param_mode) {
+        project_bwd_kernel<true><<<blocks, threads, 0, st>>>(
+            n, xyz, scaling_log, rotation, nullptr, opacity, opacity_is_logit, feat0, feat_stride, cam,
+            (const float2*)g_means2d, (const float4*)g_conics, g_depths, g_colors, g_opacities, g_xyz, g_scaling_log,
+            (float4*)g_rotation, nullptr, g_opacity, g_feat0, g_feat_stride);
+    } else {
+        project_bwd_kernel<false><<<blocks, threads, 0, st>>>(
+            n, xyz, nullptr, nullptr, cov3d, opacity, opacity_is_logit, feat0, feat_stride, cam,
+            (const float2*)g_means2d, (const float4*)g_conics, g_depths, g_colors, g_opacities, g_xyz, nullptr, nullptr,
+            g_cov3d, g_opacity, g_feat0, g_feat_stride);
+    }
+    GS_CUDA_TRY(cudaGetLastError());
+    return GS_OK;
+}

@@ -1,0 +1,319 @@
+"""Drop-in for the reference's differentiable renderer (src/core/renderer.py).
+
+Same public surface -- ``RenderSettings`` (renderer.py:13-20), ``GaussianRenderer(tile_size,
+radius_min, radius_max)`` (renderer.py:24-28) and ``render(camera, gaussians, settings)``
+(renderer.py:31-114) returning ``image, alpha, depth, viewspace_points, visibility_filter,
+radii, conics`` with autograd intact -- but every stage runs in hand-written sm_100a kernels
+behind the C ABI of ``include/gsplat_b200.h``.  Host code here is plumbing only: two
+``torch.autograd.Function``s around the projection and compositing kernels with the
+non-differentiable depth sort / tile binning between them.
+
+CUDA only.  There is deliberately no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+_U8 = torch.uint8
+_I32 = torch.int32
+_I64 = torch.int64
+_F32 = torch.float32
+
+
+@dataclass
+class RenderSettings:
+    """Render settings; field for field the reference's dataclass (renderer.py:13-20)."""
+    image_height: int
+    image_width: int
+    bg_color: torch.Tensor
+    scale_modifier: float = 1.0   # never read by the reference renderer either
+    debug: bool = False
+
+
+class _ViewMeta:
+    """Per-call constants shared by forward and backward of the two Functions."""
+
+    __slots__ = ("cam", "W", "H", "tile", "rmin", "rmax", "param_mode", "opacity_is_logit",
+                 "feat_stride", "stream_of")
+
+    def __init__(self):
+        self.cam = None
+
+
+def _camera_block(camera) -> ctypes.Array:
+    """renderer.py:140-152: intrinsics in python float64 rounded once to fp32; W2C rotation and
+    translation.  16 host floats (GS_CAMERA_FLOATS)."""
+    W, H = camera._width, camera._height
+    fx = np.float32(0.5 * W / math.tan(camera._FoVx * 0.5))
+    fy = np.float32(0.5 * H / math.tan(camera._FoVy * 0.5))
+    cx = np.float32(W * 0.5)
+    cy = np.float32(H * 0.5)
+    WV = camera.world_view_transform()
+    wv = WV.detach().to(device="cpu", dtype=_F32).numpy()
+    vals = list(wv[:3, :3].reshape(-1)) + list(wv[:3, 3]) + [fx, fy, cx, cy]
+    return (ctypes.c_float * 16)(*[float(v) for v in vals])
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _ProjectFn(torch.autograd.Function):
+    """Stage P+M+C (gs_project_fwd / gs_project_bwd)."""
+
+    @staticmethod
+    def forward(ctx, meta, xyz, scaling, rotation, cov3d, opacity, feat_src, features_rest):
+        lib = _lib.load()
+        n = xyz.shape[0]
+        dev = xyz.device
+        new = lambda *shape, dtype=_F32: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
+        means2d, depths, conics, radii = new(n, 2), new(n), new(n, 2, 2), new(n)
+        colors, opac = new(n, 3), new(n)
+        vis = new(n, dtype=_U8)
+        tiles_touched = new(n, dtype=_I32)
+        tile_rect = new(n, 4, dtype=torch.int16)
+        depth_keys = new(n, dtype=_I32)
+        rec = new(n, 12)
+        check(lib.gs_project_fwd(
+            n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
+            ptr(feat_src), meta.feat_stride, meta.cam, meta.W, meta.H, meta.tile, meta.rmin, meta.rmax,
+            ptr(means2d), ptr(depths), ptr(conics), ptr(radii), ptr(colors), ptr(opac), ptr(vis),
+            ptr(tiles_touched), ptr(tile_rect), ptr(depth_keys), ptr(rec), _stream(dev)), "gs_project_fwd")
+        ctx.meta = meta
+        ctx.save_for_backward(xyz, scaling, rotation, cov3d, opacity, feat_src, features_rest)
+        vis_b = vis.view(torch.bool)
+        ctx.mark_non_differentiable(radii, vis_b, tiles_touched, tile_rect, depth_keys, rec)
+        return means2d, conics, depths, colors, opac, radii, vis_b, tiles_touched, tile_rect, depth_keys, rec
+
+    @staticmethod
+    def backward(ctx, g_means2d, g_conics, g_depths, g_colors, g_opac, *_unused):
+        lib = _lib.load()
+        meta = ctx.meta
+        xyz, scaling, rotation, cov3d, opacity, feat_src, features_rest = ctx.saved_tensors
+        n = xyz.shape[0]
+        dev = xyz.device
+
+        def dense(g, *shape):
+            if g is None:
+                return torch.zeros(shape, dtype=_F32, device=dev)
+            return g.contiguous()
+
+        g_means2d = dense(g_means2d, n, 2)
+        g_conics = dense(g_conics, n, 2, 2)
+        g_depths = dense(g_depths, n)
+        g_colors = dense(g_colors, n, 3)
+        g_opac = dense(g_opac, n)
+        g_xyz = torch.empty_like(xyz)
+        g_scaling = torch.empty_like(scaling) if meta.param_mode else None
+        g_rotation = torch.empty_like(rotation) if meta.param_mode else None
+        g_cov3d = None if meta.param_mode else torch.empty((n, 3, 3), dtype=_F32, device=dev)
+        g_opacity = torch.empty_like(opacity)
+        # only features[:,0,:] feeds the colour; every other SH row gets the dense zeros the
+        # reference's autograd produces
+        if feat_src.shape[1] == 1:
+            g_feat = torch.empty_like(feat_src)
+        else:
+            g_feat = torch.zeros_like(feat_src)
+        check(lib.gs_project_bwd(
+            n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
+            ptr(feat_src), meta.feat_stride, meta.cam,
+            ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
+            ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), ptr(g_cov3d), ptr(g_opacity),
+            ptr(g_feat), g_feat.stride(0), _stream(dev)), "gs_project_bwd")
+        g_rest = torch.zeros_like(features_rest) if (features_rest is not None and ctx.needs_input_grad[7]) else None
+        return None, g_xyz, g_scaling, g_rotation, g_cov3d, g_opacity, g_feat, g_rest
+
+
+class _RasterizeFn(torch.autograd.Function):
+    """Stage R (gs_raster_fwd / gs_raster_bwd).  `means2d` is the tensor returned to the caller as
+    ``viewspace_points``; its ``.grad`` after ``retain_grad()`` is what this backward emits."""
+
+    @staticmethod
+    def forward(ctx, meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, any_visible):
+        lib = _lib.load()
+        dev = means2d.device
+        H, W = meta.H, meta.W
+        tiles = tile_ranges.shape[0]
+        image = torch.empty((3, H, W), dtype=_F32, device=dev)
+        alpha = torch.empty((1, H, W), dtype=_F32, device=dev)
+        depth = torch.empty((1, H, W), dtype=_F32, device=dev)
+        pix_state = torch.empty((H * W, 4), dtype=_F32, device=dev)
+        n_consumed = torch.empty((H, W), dtype=_I32, device=dev)
+        tile_consumed = torch.empty((tiles,), dtype=_I32, device=dev)
+        check(lib.gs_raster_fwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), int(any_visible),
+                                ptr(image), ptr(alpha), ptr(depth), ptr(pix_state), ptr(n_consumed),
+                                ptr(tile_consumed), _stream(dev)), "gs_raster_fwd")
+        ctx.meta = meta
+        ctx.any_visible = any_visible
+        ctx.n = means2d.shape[0]
+        ctx.save_for_backward(rec, entry_ids, tile_ranges, bg, alpha, pix_state, n_consumed, tile_consumed)
+        ctx.mark_non_differentiable(n_consumed, tile_consumed)
+        return image, alpha, depth, n_consumed, tile_consumed
+
+    @staticmethod
+    def backward(ctx, g_image, g_alpha, g_depth, *_unused):
+        lib = _lib.load()
+        meta = ctx.meta
+        rec, entry_ids, tile_ranges, bg, alpha, pix_state, n_consumed, tile_consumed = ctx.saved_tensors
+        n = ctx.n
+        dev = rec.device
+        H, W = meta.H, meta.W
+        # one zeroed slab carved into the five contiguous gradient tensors (atomics accumulate into it)
+        slab = torch.zeros(n * 11, dtype=_F32, device=dev)
+        g_means2d = slab[0:2 * n].view(n, 2)
+        g_conics = slab[2 * n:6 * n].view(n, 2, 2)
+        g_depths = slab[6 * n:7 * n]
+        g_colors = slab[7 * n:10 * n].view(n, 3)
+        g_opac = slab[10 * n:11 * n]
+        if ctx.any_visible and entry_ids.numel() > 0:
+            def dense(g, c):
+                if g is None:
+                    return torch.zeros((c, H, W), dtype=_F32, device=dev)
+                return g.contiguous()
+
+            check(lib.gs_raster_bwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), ptr(alpha),
+                                    ptr(pix_state), ptr(n_consumed), ptr(tile_consumed),
+                                    ptr(dense(g_image, 3)), ptr(dense(g_alpha, 1)), ptr(dense(g_depth, 1)),
+                                    ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
+                                    _stream(dev)), "gs_raster_bwd")
+        return None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None, None, None
+
+
+def _is_parameter_model(g) -> bool:
+    """True for objects laid out like the reference's GaussianModel (gaussian_model.py:21-40):
+    raw parameters plus the exp / sigmoid / normalize activations, which the projection kernel
+    can fuse.  Anything else goes through the duck-typed accessors."""
+    names = ("_xyz", "_scaling", "_rotation", "_opacity", "_features_dc")
+    if not all(isinstance(getattr(g, a, None), torch.Tensor) for a in names):
+        return False
+    return (getattr(g, "scaling_activation", None) is torch.exp
+            and getattr(g, "opacity_activation", None) is torch.sigmoid
+            and getattr(g, "rotation_activation", None) is torch.nn.functional.normalize)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != _F32:
+        raise TypeError(f"expected float32 tensors, got {t.dtype}")
+    return t.contiguous()
+
+
+class GaussianRenderer:
+    """3D Gaussian differentiable renderer -- B200 implementation of renderer.py:22-367."""
+
+    def __init__(self, tile_size: int = 16, radius_min: float = 0.01, radius_max: float = 50.0):
+        self.tile_size = tile_size
+        self.radius_min = radius_min
+        self.radius_max = radius_max
+        self.device = torch.device("cuda")
+        self.last_stats: Dict[str, int] = {}
+        _lib.load()   # fail at construction, not at first render, if the extension is missing
+
+    # ------------------------------------------------------------------------------------
+    def render(self, camera, gaussians, settings: RenderSettings) -> Dict[str, torch.Tensor]:
+        """Main render method; same contract as the reference (renderer.py:31-114).
+
+        camera:    object with ``_width, _height, _FoVx, _FoVy`` and a callable
+                   ``world_view_transform()`` -> 4x4 world-to-camera tensor.
+        gaussians: either a GaussianModel-shaped object (raw ``_xyz/_scaling/_rotation/_opacity/
+                   _features_dc`` + the reference's activations), or any object exposing
+                   ``get_xyz, get_covariance, get_features, get_opacity``.
+        """
+        xyz = gaussians.get_xyz
+        device = xyz.device
+        if device.type != "cuda":
+            raise RuntimeError("GaussianRenderer (B200) renders CUDA tensors only; there is no CPU fallback "
+                               f"(gaussians.get_xyz is on {device})")
+        H, W = int(settings.image_height), int(settings.image_width)
+        with torch.cuda.device(device):
+            return self._render(camera, gaussians, settings, device, H, W)
+
+    def _render(self, camera, gaussians, settings, device, H, W):
+        lib = _lib.load()
+        T = int(self.tile_size)
+        bg = settings.bg_color.detach().to(device=device, dtype=_F32).reshape(3).contiguous()
+
+        meta = _ViewMeta()
+        meta.cam = _camera_block(camera)
+        meta.W, meta.H, meta.tile = W, H, T
+        meta.rmin, meta.rmax = float(self.radius_min), float(self.radius_max)
+
+        # ---- stage P+M+C -------------------------------------------------------------------
+        if _is_parameter_model(gaussians):
+            meta.param_mode, meta.opacity_is_logit = True, True
+            xyz = _f32c(gaussians._xyz)
+            scaling, rotation = _f32c(gaussians._scaling), _f32c(gaussians._rotation)
+            opacity = _f32c(gaussians._opacity)
+            feat_src = _f32c(gaussians._features_dc)
+            rest = getattr(gaussians, "_features_rest", None)
+            if rest is not None and rest.numel() == 0:
+                rest = None
+            cov3d = None
+        else:
+            meta.param_mode, meta.opacity_is_logit = False, False
+            xyz = _f32c(gaussians.get_xyz)
+            cov3d = _f32c(gaussians.get_covariance)
+            feats = gaussians.get_features
+            if not (feats.dim() == 3 and feats.shape[1] >= 1):          # renderer.py:89-92
+                feats = gaussians._features_dc
+            feat_src = _f32c(feats)
+            opacity = _f32c(gaussians.get_opacity)
+            scaling = rotation = rest = None
+        n = xyz.shape[0]
+        if feat_src.dim() != 3 or feat_src.shape[0] != n or feat_src.shape[2] != 3:
+            raise ValueError(f"features must be [N,K,3], got {tuple(feat_src.shape)}")
+        if opacity.numel() != n:
+            raise ValueError(f"opacity must have N={n} elements, got {tuple(opacity.shape)}")
+        meta.feat_stride = feat_src.stride(0)
+
+        (means2d, conics, depths, colors, opac, radii, vis, tiles_touched, tile_rect, depth_keys,
+         rec) = _ProjectFn.apply(meta, xyz, scaling, rotation, cov3d, opacity, feat_src, rest)
+
+        # ---- stage S+B (non-differentiable) --------------------------------------------------
+        tiles_x, tiles_y = (W + T - 1) // T, (H + T - 1) // T
+        num_tiles = tiles_x * tiles_y
+        stream = _stream(device)
+        counters = torch.empty(3, dtype=_I64, device=device)
+        sorted_ids = torch.empty(n, dtype=_I32, device=device)
+        offsets = torch.empty(n, dtype=_I64, device=device)
+        ws_bytes = int(lib.gs_bin_workspace_bytes(n, 0, num_tiles))
+        ws = torch.empty(ws_bytes, dtype=_U8, device=device)
+        check(lib.gs_bin_prepare(n, ptr(depth_keys), ptr(tiles_touched), ptr(ws), ws_bytes, ptr(sorted_ids),
+                                 ptr(offsets), ptr(counters), stream), "gs_bin_prepare")
+        # the one host sync of the frame (the reference syncs on vis_mask.sum() at renderer.py:74)
+        num_sorted, D, num_vis = (int(v) for v in counters.tolist())
+        tile_ranges = torch.empty((num_tiles, 2), dtype=_I32, device=device)
+        entry_ids = torch.empty(max(D, 1), dtype=_I32, device=device)
+        ws_bytes = int(lib.gs_bin_workspace_bytes(0, D, num_tiles))
+        if ws.numel() < ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=_U8, device=device)
+        check(lib.gs_bin_sort(n, num_sorted, D, ptr(sorted_ids), ptr(offsets), ptr(tile_rect), ptr(depth_keys),
+                              tiles_x, num_tiles, ptr(ws), ws.numel(), ptr(entry_ids), ptr(tile_ranges), None,
+                              stream), "gs_bin_sort")
+        entry_ids = entry_ids[:D]
+
+        # ---- stage R -----------------------------------------------------------------------
+        image, alpha, depth, n_consumed, tile_consumed = _RasterizeFn.apply(
+            meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, num_vis > 0)
+
+        self.last_stats = {"num_visible": num_vis, "num_binned": num_sorted, "tile_pairs": D}
+        self._last_debug = {"tile_consumed": tile_consumed, "n_consumed": n_consumed, "entry_ids": entry_ids,
+                            "tile_ranges": tile_ranges, "depths": depths, "tiles_touched": tiles_touched,
+                            "tile_rect": tile_rect, "depth_keys": depth_keys, "sorted_ids": sorted_ids[:num_sorted]}
+        return {
+            "image": image,
+            "alpha": alpha,
+            "depth": depth,
+            "viewspace_points": means2d,
+            "visibility_filter": vis,
+            "radii": radii,
+            "conics": conics,
+        }

@@ -1,0 +1,277 @@
+"""Generate golden fixtures by running the *literal, unmodified* reference renderer.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py [case ...]
+
+For every case it
+  1. builds a seeded synthetic scene (oracle.splat_oracle generators = SURVEY 8d scenes),
+  2. renders it with /root/reference's GaussianRenderer.render through the duck-typed adapters the
+     reference's own test uses (tests/test_renderer.py:7-53), forward + autograd backward,
+  3. stores inputs, outputs and gradients as tests/golden/<case>.npz,
+  4. prints how far the oracle restatement is from the literal reference.
+
+The fixtures are small (N <= 400, <= 128x96) because the reference's pixel loop costs ~190 us per
+(pixel x list entry) and its autograd backward is super-linear.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+from oracle import splat_oracle as so  # noqa: E402
+
+
+def import_reference():
+    sys.path.insert(0, "/root/reference")
+    with contextlib.redirect_stdout(io.StringIO()):      # config/config.py prints on import
+        from src.core.renderer import GaussianRenderer, RenderSettings
+        from src.core.gaussian_model import GaussianModel
+        from config.config import TrainingConfig
+    return GaussianRenderer, RenderSettings, GaussianModel, TrainingConfig
+
+
+class RefCamera:
+    """4 attributes + a callable, exactly what renderer.py:140-152 reads."""
+
+    def __init__(self, cam: so.OracleCamera):
+        self._width, self._height = cam.width, cam.height
+        self._FoVx, self._FoVy = cam.fovx, cam.fovy
+        self._WV = cam.world_view
+
+    def world_view_transform(self):
+        return self._WV
+
+
+class RefGaussians:
+    """Forwards to a real reference GaussianModel; get_covariance -> compute_3d_covariance()
+    because the model's own property is broken (gaussian_model.py:124-128)."""
+
+    def __init__(self, model):
+        self.m = model
+
+    get_xyz = property(lambda s: s.m.get_xyz)
+    get_opacity = property(lambda s: s.m.get_opacity)
+    get_features = property(lambda s: s.m.get_features)
+    get_covariance = property(lambda s: s.m.compute_3d_covariance())
+
+    @property
+    def _features_dc(self):
+        return self.m._features_dc
+
+
+class CovGaussians:
+    """The reference test's DummyGaussians shape: covariance handed over directly."""
+
+    def __init__(self, xyz, cov3d, features, opacity):
+        self._xyz, self._cov, self._features, self._opacity = xyz, cov3d, features, opacity
+
+    get_xyz = property(lambda s: s._xyz)
+    get_opacity = property(lambda s: s._opacity)
+    get_features = property(lambda s: s._features)
+    get_covariance = property(lambda s: s._cov)
+
+
+# ---------------------------------------------------------------------------------------------
+# case table
+# ---------------------------------------------------------------------------------------------
+CASES = {
+    # name: dict(scene, n, seed, W, H, cam, bg, scale_boost (added to log-scale), opacity_boost)
+    "aniso_n120_48x40_orbit": dict(scene="aniso", n=120, seed=3, W=48, H=40, cam=("orbit", 1, 8),
+                                   bg=(0.25, 0.1, 0.4), scale_boost=math.log(8.0), opacity_boost=0.0),
+    "refinit_n300_64x64_saturating": dict(scene="ref", n=300, seed=0, W=64, H=64, cam=("c0",),
+                                          bg=(0.0, 0.0, 0.0), scale_boost=math.log(6.0), opacity_boost=3.0),
+    "aniso_n80_40x40_rot": dict(scene="aniso", n=80, seed=5, W=40, H=40, cam=("orbit", 3, 7),
+                                bg=(0.25, 0.1, 0.4), scale_boost=math.log(10.0), opacity_boost=1.0),
+    "aniso_n200_96x64_bigsplats": dict(scene="aniso", n=200, seed=11, W=96, H=64, cam=("c0",),
+                                       bg=(0.6, 0.6, 0.6), scale_boost=math.log(25.0), opacity_boost=-1.0),
+}
+
+
+def build_scene(spec):
+    gen = so.scene_aniso if spec["scene"] == "aniso" else so.scene_ref_init
+    s = gen(spec["n"], spec["seed"])
+    s["scaling"] = s["scaling"] + spec["scale_boost"]
+    s["opacity"] = s["opacity"] + spec["opacity_boost"]
+    if spec["cam"][0] == "c0":
+        cam = so.camera_c0(spec["W"], spec["H"])
+    else:
+        cam = so.camera_orbit(spec["cam"][1], spec["cam"][2], spec["W"], spec["H"])
+    return s, cam
+
+
+def run_reference(spec, s, cam):
+    GaussianRenderer, RenderSettings, GaussianModel, TrainingConfig = import_reference()
+    m = GaussianModel(TrainingConfig())
+    P = torch.nn.Parameter
+    m._xyz, m._features_dc, m._features_rest = P(s["xyz"].clone()), P(s["features_dc"].clone()), P(s["features_rest"].clone())
+    m._scaling, m._rotation, m._opacity = P(s["scaling"].clone()), P(s["rotation"].clone()), P(s["opacity"].clone())
+    H, W = spec["H"], spec["W"]
+    settings = RenderSettings(image_height=H, image_width=W, bg_color=torch.tensor(spec["bg"], dtype=torch.float32))
+    rd = GaussianRenderer(tile_size=16, radius_min=0.01, radius_max=50.0)
+    t0 = time.time()
+    out = rd.render(RefCamera(cam), RefGaussians(m), settings)
+    t_fwd = time.time() - t0
+    out["viewspace_points"].retain_grad()
+    weights = so.loss_weights(H, W)
+    loss = so.weighted_loss(out, weights)
+    t0 = time.time()
+    loss.backward()
+    t_bwd = time.time() - t0
+    # the reference's own stages again, for the intermediate tensors render() does not return
+    with torch.no_grad():
+        proj = rd._project_gaussians_3d_to_2d(RefCamera(cam), RefGaussians(m))
+        vis = rd._frustum_culling(proj["means2D"], proj["depths"], proj["radii"], settings)
+        sorted_idx = rd._sort_gaussians_by_depth(vis, proj["depths"]) if int(vis.sum()) else torch.zeros(0, dtype=torch.int64)
+    d = proj["depths"][vis]
+    n_ties = int(d.numel() - torch.unique(d).numel())
+    res = {
+        "image": out["image"], "alpha": out["alpha"], "depth": out["depth"],
+        "means2D": out["viewspace_points"], "conics": out["conics"], "radii": out["radii"],
+        "vis": out["visibility_filter"], "depths": proj["depths"], "cov2D": proj["cov2D"],
+        "sorted_idx": sorted_idx, "loss": loss.detach(),
+        "g_xyz": m._xyz.grad, "g_scaling": m._scaling.grad, "g_rotation": m._rotation.grad,
+        "g_opacity": m._opacity.grad, "g_features_dc": m._features_dc.grad,
+        "g_features_rest_absmax": m._features_rest.grad.abs().max(),
+        "g_means2D": out["viewspace_points"].grad,
+    }
+    return res, t_fwd, t_bwd, n_ties
+
+
+def run_oracle(spec, s, cam):
+    leaf = {k: s[k].clone().requires_grad_(True) for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
+    H, W = spec["H"], spec["W"]
+    out = so.render_from_params(cam, leaf["xyz"], leaf["scaling"], leaf["rotation"], leaf["opacity"],
+                                leaf["features_dc"], torch.tensor(spec["bg"]), H, W, return_stats=True)
+    out["viewspace_points"].retain_grad()
+    loss = so.weighted_loss(out, so.loss_weights(H, W))
+    loss.backward()
+    return out, leaf, loss
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def make_case(name):
+    spec = CASES[name]
+    s, cam = build_scene(spec)
+    ref, t_fwd, t_bwd, n_ties = run_reference(spec, s, cam)
+    assert n_ties == 0, f"{name}: {n_ties} visible depth ties; the reference sort order would be unspecified"
+    o, leaf, oloss = run_oracle(spec, s, cam)
+    print(f"[{name}] reference fwd {t_fwd:.1f}s bwd {t_bwd:.1f}s  visible {int(ref['vis'].sum())}/{spec['n']}"
+          f"  saturated px {int((ref['alpha'] >= 0.995).sum())}  clamped ch {int((ref['image'] >= 1).sum())}")
+    print("   oracle vs literal:  image %.2e  alpha %.2e  depth %.2e  means2D %.2e (bit-equal %.4f)  depths bit-equal %.4f" % (
+        float((o["image"] - ref["image"]).abs().max()), float((o["alpha"] - ref["alpha"]).abs().max()),
+        float((o["depth"] - ref["depth"]).abs().max()), float((o["viewspace_points"] - ref["means2D"]).abs().max()),
+        float((o["viewspace_points"].detach().view(torch.int32) == ref["means2D"].detach().view(torch.int32)).float().mean()),
+        float((o["depths"].detach().view(torch.int32) == ref["depths"].view(torch.int32)).float().mean())))
+    print("   radii max rel %.2e  int(radii) mismatches %d  vis mismatches %d  sorted order equal %s" % (
+        rel(o["radii"], ref["radii"]), int((o["radii"].detach().int() != ref["radii"].detach().int()).sum()),
+        int((o["visibility_filter"] != ref["vis"]).sum()),
+        bool(torch.equal(so.sort_by_depth(o["visibility_filter"], o["depths"]), ref["sorted_idx"]))))
+    print("   grads rel: xyz %.2e scaling %.2e rotation %.2e opacity %.2e dc %.2e means2D %.2e" % (
+        rel(leaf["xyz"].grad, ref["g_xyz"]), rel(leaf["scaling"].grad, ref["g_scaling"]),
+        rel(leaf["rotation"].grad, ref["g_rotation"]), rel(leaf["opacity"].grad, ref["g_opacity"]),
+        rel(leaf["features_dc"].grad, ref["g_features_dc"]), rel(o["viewspace_points"].grad, ref["g_means2D"])))
+    save = {"in_" + k: s[k].numpy() for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
+    save.update({"cam_WV": cam.world_view.numpy(), "cam_fov": np.array([cam.fovx, cam.fovy], dtype=np.float64),
+                 "size_WH": np.array([spec["W"], spec["H"]]), "bg": np.array(spec["bg"], dtype=np.float32)})
+    save.update({"ref_" + k: v.detach().numpy() for k, v in ref.items()})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+
+
+def make_kat_two_splats():
+    """The reference's own known-answer scene (tests/test_renderer.py:127-161), through the
+    covariance-input path, with gradients added."""
+    GaussianRenderer, RenderSettings, _, _ = import_reference()
+    H = W = 64
+    xyz = torch.tensor([[0.0, 0.0, 1.0], [0.0, 0.0, 2.0]], requires_grad=True)
+    sig = torch.full((2, 3), 0.01)
+    cov = torch.diag_embed(sig ** 2).requires_grad_(True)
+    feats = torch.zeros(2, 16, 3)
+    feats[0, 0, 0] = 1.0
+    feats[1, 0, 1] = 1.0
+    feats.requires_grad_(True)
+    op = torch.tensor([[0.5], [0.5]], requires_grad=True)
+    cam = so.OracleCamera(W, H, math.radians(60.0), math.radians(60.0), torch.eye(4))
+    settings = RenderSettings(image_height=H, image_width=W, bg_color=torch.zeros(3))
+    out = GaussianRenderer().render(RefCamera(cam), CovGaussians(xyz, cov, feats, op), settings)
+    out["viewspace_points"].retain_grad()
+    loss = so.weighted_loss(out, so.loss_weights(H, W))
+    loss.backward()
+    save = dict(in_xyz=xyz.detach().numpy(), in_cov3d=cov.detach().numpy(), in_features=feats.detach().numpy(),
+                in_opacity=op.detach().numpy(), cam_WV=np.eye(4, dtype=np.float32),
+                cam_fov=np.array([cam.fovx, cam.fovy]), size_WH=np.array([W, H]), bg=np.zeros(3, np.float32),
+                ref_image=out["image"].detach().numpy(), ref_alpha=out["alpha"].detach().numpy(),
+                ref_depth=out["depth"].detach().numpy(), ref_means2D=out["viewspace_points"].detach().numpy(),
+                ref_conics=out["conics"].detach().numpy(), ref_radii=out["radii"].detach().numpy(),
+                ref_vis=out["visibility_filter"].numpy(), ref_loss=loss.detach().numpy(),
+                ref_g_xyz=xyz.grad.numpy(), ref_g_cov3d=cov.grad.numpy(), ref_g_features=feats.grad.numpy(),
+                ref_g_opacity=op.grad.numpy(), ref_g_means2D=out["viewspace_points"].grad.numpy())
+    np.savez_compressed(os.path.join(HERE, "kat_two_splats_64x64.npz"), **save)
+    cy = cx = 32
+    print("[kat_two_splats] centre alpha %.6f rgb %s depth %.6f" % (
+        float(out["alpha"][0, cy, cx].detach()), out["image"][:, cy, cx].tolist(), float(out["depth"][0, cy, cx].detach())))
+
+
+def make_stage_fixture(n=200000, seed=0):
+    """Stages 1-3 of the literal reference on the bench scene geometry (1080p, C0 and one orbit
+    view), reduced to what pins the integer outputs: int radii, visibility mask, depth bits,
+    tile rectangles.  Stored for a strided subset so the file stays small."""
+    GaussianRenderer, RenderSettings, GaussianModel, TrainingConfig = import_reference()
+    W, H = 1920, 1080
+    for tag, cam in (("c0", so.camera_c0(W, H)), ("orbit5of16", so.camera_orbit(5, 16, W, H))):
+        s = so.scene_aniso(n, seed)
+        m = GaussianModel(TrainingConfig())
+        P = torch.nn.Parameter
+        m._xyz, m._features_dc, m._features_rest = P(s["xyz"]), P(s["features_dc"]), P(s["features_rest"])
+        m._scaling, m._rotation, m._opacity = P(s["scaling"]), P(s["rotation"]), P(s["opacity"])
+        rd = GaussianRenderer()
+        settings = RenderSettings(image_height=H, image_width=W, bg_color=torch.zeros(3))
+        with torch.no_grad():
+            proj = rd._project_gaussians_3d_to_2d(RefCamera(cam), RefGaussians(m))
+            vis = rd._frustum_culling(proj["means2D"], proj["depths"], proj["radii"], settings)
+            cov3d = so.covariance_3d(s["scaling"], s["rotation"])
+            o = so.project(s["xyz"], cov3d, cam)
+            ovis = so.cull(o["means2D"], o["depths"], o["radii"], H, W)
+        print(f"[stages_{tag}] N={n}: means2D bit-equal {float((o['means2D'].view(torch.int32) == proj['means2D'].view(torch.int32)).float().mean()):.6f}"
+              f"  depths bit-equal {float((o['depths'].view(torch.int32) == proj['depths'].view(torch.int32)).float().mean()):.6f}"
+              f"  radii rel {rel(o['radii'], proj['radii']):.2e} closed-form rel {rel(so.radii_closed_form(o['cov2D']), proj['radii']):.2e}"
+              f"  int(radii) mism {int((o['radii'].int() != proj['radii'].int()).sum())}"
+              f"  closed-form int mism {int((so.radii_closed_form(o['cov2D']).int() != proj['radii'].int()).sum())}"
+              f"  vis mism {int((ovis != vis).sum())}  conics rel {rel(o['conics'], proj['conics']):.2e}")
+        tx0, tx1, ty0, ty1, cnt = so.tile_rects(proj["means2D"], proj["radii"], H, W)
+        np.savez_compressed(
+            os.path.join(HERE, f"stages_aniso_n{n}_1080p_{tag}.npz"),
+            n=np.array(n), seed=np.array(seed), cam_WV=cam.world_view.numpy(), cam_fov=np.array([cam.fovx, cam.fovy]),
+            size_WH=np.array([W, H]),
+            ref_means2D_bits=proj["means2D"].numpy().view(np.uint32), ref_depth_bits=proj["depths"].numpy().view(np.uint32),
+            ref_radii=proj["radii"].numpy(), ref_vis=np.packbits(vis.numpy()),
+            ref_conics_sub=proj["conics"].numpy()[::16],
+            ref_rect=torch.stack([tx0, tx1, ty0, ty1], 1).numpy().astype(np.int16), ref_cnt=cnt.numpy().astype(np.int16))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    want = sys.argv[1:] or (["kat", "stages"] + list(CASES))
+    for c in want:
+        if c == "kat":
+            make_kat_two_splats()
+        elif c == "stages":
+            make_stage_fixture()
+        else:
+            make_case(c)

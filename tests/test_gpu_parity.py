@@ -1,0 +1,444 @@
+"""GPU: the CUDA path, called through GaussianRenderer.render -> C ABI, against
+  (1) the reference's own known-answer tests (tests/test_renderer.py:95-161 restated for cuda),
+  (2) fixtures recorded from the literal reference (tests/golden/*.npz),
+  (3) the CPU oracle on seeded scenes the oracle finishes in seconds,
+  (4) size-independent properties at BASELINE.json's full size (1M splats, 1080p).
+
+Tolerances are the ones BASELINE.json's north_star states: integer radii / visibility / sort keys /
+tile ranges exact; image, alpha, depth 1e-4 absolute; parameter gradients 1e-3 relative
+(max|g - g_ref| <= 1e-3 max|g_ref|).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import splat_oracle as so
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+# ----------------------------------------------------------------------------------------------
+# (1) the reference's own KATs, on cuda, through duck-typed stand-ins
+# ----------------------------------------------------------------------------------------------
+class StubCamera:
+    def __init__(self, width=64, height=64, fov_deg=60.0, device="cuda"):
+        self._width, self._height = width, height
+        self._FoVx = self._FoVy = math.radians(fov_deg)
+        self._WV = torch.eye(4, dtype=torch.float32, device=device)
+
+    def world_view_transform(self):
+        return self._WV
+
+
+class StubGaussians:
+    """get_xyz / get_opacity / get_features [N,16,3] / get_covariance = diag(sigma^2): the
+    shape of the reference test's stand-in, i.e. the covariance-input path."""
+
+    def __init__(self, xyz, sigmas, colors_dc, opacities, device="cuda"):
+        f = lambda v: torch.as_tensor(v, dtype=torch.float32, device=device)  # noqa: E731
+        self._xyz, self._sig = f(xyz), f(sigmas)
+        self._features = torch.zeros((self._xyz.shape[0], 16, 3), dtype=torch.float32, device=device)
+        self._features[:, 0, :] = f(colors_dc)
+        self._opacity = f(opacities).view(-1, 1)
+
+    get_xyz = property(lambda s: s._xyz)
+    get_opacity = property(lambda s: s._opacity)
+    get_features = property(lambda s: s._features)
+    get_covariance = property(lambda s: torch.diag_embed(s._sig ** 2))
+
+
+@pytest.fixture()
+def kat():
+    import gsplat_b200 as gb
+    return gb.GaussianRenderer(tile_size=16, radius_min=0.01, radius_max=50.0), gb.RenderSettings(
+        image_height=64, image_width=64, bg_color=torch.zeros(3, device="cuda"), scale_modifier=1.0, debug=True)
+
+
+def test_kat_shapes_and_types(kat):
+    rd, settings = kat
+    gs = StubGaussians([[0.0, 0.0, 1.0]], [[0.01, 0.01, 0.01]], [[1.0, 1.0, 1.0]], [0.8])
+    out = rd.render(StubCamera(), gs, settings)
+    assert out["image"].shape == (3, 64, 64) and out["alpha"].shape == (1, 64, 64) and out["depth"].shape == (1, 64, 64)
+    assert out["viewspace_points"].shape[1] == 2
+    assert out["visibility_filter"].dtype == torch.bool
+    assert out["radii"].ndim == 1
+    assert out["conics"].shape[-2:] == (2, 2)
+    assert set(out) == {"image", "alpha", "depth", "viewspace_points", "visibility_filter", "radii", "conics"}
+    assert all(v.is_cuda for v in out.values())
+
+
+def test_kat_culling_all_behind(kat):
+    rd, settings = kat
+    gs = StubGaussians([[0.0, 0.0, -1.0], [0.0, 0.0, -2.0]], [[0.01] * 3] * 2, [[1.0, 0, 0], [0, 1.0, 0]], [0.5, 0.5])
+    out = rd.render(StubCamera(32, 32), gs, settings)
+    bg = settings.bg_color.view(3, 1, 1).repeat(1, 64, 64)
+    assert torch.allclose(out["image"], bg)
+    assert int(torch.count_nonzero(out["alpha"])) == 0
+
+
+def test_kat_front_to_back_blending_center_pixel(kat):
+    rd, settings = kat
+    gs = StubGaussians([[0.0, 0.0, 1.0], [0.0, 0.0, 2.0]], [[0.01] * 3] * 2, [[1.0, 0, 0], [0, 1.0, 0]], [0.5, 0.5])
+    out = rd.render(StubCamera(), gs, settings)
+    rgb, a, d = out["image"][:, 32, 32], out["alpha"][0, 32, 32], out["depth"][0, 32, 32]
+    assert abs(float(a) - 0.75) < 1e-3
+    exp = 0.5 * torch.sigmoid(torch.tensor([1.0, 0, 0])) + 0.25 * torch.sigmoid(torch.tensor([0, 1.0, 0]))
+    assert torch.allclose(rgb.cpu(), exp, atol=1e-3)
+    assert abs(float(d) - 4 / 3) < 2e-2
+
+
+def test_kat_fixture_covariance_path_with_gradients():
+    """Same scene, full image + gradients of the covariance-input path vs the literal reference."""
+    import gsplat_b200 as gb
+    d = util.load_golden("kat_two_splats_64x64")
+
+    class G:
+        pass
+    g = G()
+    xyz = torch.tensor(d["in_xyz"], device="cuda", requires_grad=True)
+    cov = torch.tensor(d["in_cov3d"], device="cuda", requires_grad=True)
+    feats = torch.tensor(d["in_features"], device="cuda", requires_grad=True)
+    op = torch.tensor(d["in_opacity"], device="cuda", requires_grad=True)
+    g.get_xyz, g.get_covariance, g.get_features, g.get_opacity = xyz, cov, feats, op
+    cam = util.cuda_camera(util.golden_camera(d))
+    out = gb.GaussianRenderer().render(cam, g, gb.RenderSettings(64, 64, torch.zeros(3)))
+    out["viewspace_points"].retain_grad()
+    loss = so.weighted_loss(out, tuple(t.cuda() for t in so.loss_weights(64, 64)))
+    loss.backward()
+    for k in ("image", "alpha", "depth"):
+        assert util.max_abs(out[k], torch.tensor(d["ref_" + k])) < IMG_TOL, k
+    assert util.rel_err(xyz.grad, torch.tensor(d["ref_g_xyz"])) < GRAD_TOL
+    assert util.rel_err(cov.grad, torch.tensor(d["ref_g_cov3d"])) < GRAD_TOL
+    assert util.rel_err(feats.grad, torch.tensor(d["ref_g_features"])) < GRAD_TOL
+    assert util.rel_err(op.grad, torch.tensor(d["ref_g_opacity"])) < GRAD_TOL
+    assert util.rel_err(out["viewspace_points"].grad, torch.tensor(d["ref_g_means2D"])) < GRAD_TOL
+    assert float(feats.grad[:, 1:, :].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------
+# (2) fixtures from the literal reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", util.RENDER_CASES)
+def test_golden_render_forward_and_gradients(name):
+    if not util.golden_available(name):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(name)
+    cam = util.golden_camera(d)
+    params = util.golden_params(d)
+    out, grads, loss, rd, m = util.cuda_render_with_grads(cam, params, torch.tensor(d["bg"]))
+    # integer / index outputs: exact
+    assert np.array_equal(out["visibility_filter"].cpu().numpy(), d["ref_vis"])
+    assert np.array_equal(out["radii"].detach().cpu().numpy().astype(np.int64), d["ref_radii"].astype(np.int64))
+    assert np.array_equal(out["viewspace_points"].detach().cpu().numpy().view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert torch.equal(rd._last_debug["sorted_ids"].cpu().long(), torch.tensor(d["ref_sorted_idx"]))
+    assert util.rel_err(out["radii"], torch.tensor(d["ref_radii"])) < 1e-6
+    assert util.rel_err(out["conics"], torch.tensor(d["ref_conics"])) < 1e-5
+    # images
+    for k in ("image", "alpha", "depth"):
+        assert util.max_abs(out[k], torch.tensor(d["ref_" + k])) < IMG_TOL, k
+    # gradients
+    for k in ("xyz", "scaling", "opacity", "features_dc"):
+        assert util.rel_err(grads[k], torch.tensor(d["ref_g_" + k])) < GRAD_TOL, k
+    assert util.rel_err(grads["means2D"], torch.tensor(d["ref_g_means2D"])) < GRAD_TOL
+    if not util.is_isotropic(d["in_scaling"]):
+        assert util.rel_err(grads["rotation"], torch.tensor(d["ref_g_rotation"])) < GRAD_TOL
+    # DC-only colour: the SH rest block receives dense zeros, not None
+    assert grads["features_rest"] is not None and float(grads["features_rest"].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["c0", "orbit5of16"])
+def test_golden_stage_integer_outputs_1080p(tag):
+    """200k anisotropic splats at 1080p: centres / depths bit-equal to the literal reference,
+    int(radii), visibility mask and tile rectangles exact."""
+    name = f"stages_aniso_n200000_1080p_{tag}"
+    if not util.golden_available(name):
+        pytest.skip("fixture not generated")
+    import gsplat_b200 as gb
+    d = util.load_golden(name)
+    cam = util.golden_camera(d)
+    s = so.scene_aniso(int(d["n"]), int(d["seed"]))
+    m = util.cuda_model_from_params(s)
+    rd = gb.GaussianRenderer()
+    with torch.no_grad():
+        out = rd.render(util.cuda_camera(cam), m, gb.RenderSettings(cam.height, cam.width, torch.zeros(3)))
+    dbg = rd._last_debug
+    assert np.array_equal(out["viewspace_points"].cpu().numpy().view(np.uint32), d["ref_means2D_bits"])
+    assert np.array_equal(dbg["depths"].cpu().numpy().view(np.uint32), d["ref_depth_bits"])
+    vis = out["visibility_filter"].cpu().numpy()
+    assert np.array_equal(np.packbits(vis), d["ref_vis"])
+    assert np.array_equal(out["radii"].cpu().numpy().astype(np.int32), d["ref_radii"].astype(np.int32))
+    assert util.rel_err(out["radii"], torch.tensor(d["ref_radii"])) < 1e-6
+    assert util.rel_err(out["conics"][::16], torch.tensor(d["ref_conics_sub"])) < 1e-5
+    rect = dbg["tile_rect"].cpu().numpy().astype(np.int64) & 0xFFFF          # tx0, ty0, tx1, ty1
+    cnt = dbg["tiles_touched"].cpu().numpy()
+    ref_rect, ref_cnt = d["ref_rect"].astype(np.int64), d["ref_cnt"].astype(np.int64)   # tx0, tx1, ty0, ty1
+    assert np.array_equal(cnt[vis], ref_cnt[vis])
+    assert int(cnt[~vis].sum()) == 0
+    sel = vis & (ref_cnt > 0)
+    assert np.array_equal(rect[sel][:, [0, 2, 1, 3]], ref_rect[sel])
+
+
+# ----------------------------------------------------------------------------------------------
+# (3) CUDA vs the oracle on seeded scenes
+# ----------------------------------------------------------------------------------------------
+ORACLE_SCENES = [
+    # name, scene fn, n, seed, W, H, camera, bg, log-scale boost, opacity boost
+    ("aniso_2k_128x96", so.scene_aniso, 2000, 21, 128, 96, ("orbit", 2, 11), (0.1, 0.2, 0.3), math.log(3.0), 0.5),
+    ("refinit_1k_100x75_ragged", so.scene_ref_init, 1000, 22, 100, 75, ("c0",), (0.0, 0.0, 0.0), math.log(5.0), 2.0),
+    ("aniso_500_33x17_tiny", so.scene_aniso, 500, 23, 33, 17, ("orbit", 5, 6), (1.0, 1.0, 1.0), math.log(2.0), 0.0),
+]
+
+
+@pytest.mark.parametrize("spec", ORACLE_SCENES, ids=[s[0] for s in ORACLE_SCENES])
+def test_cuda_matches_oracle(spec):
+    name, fn, n, seed, W, H, camspec, bg, sboost, oboost = spec
+    s = fn(n, seed)
+    s["scaling"] = s["scaling"] + sboost
+    s["opacity"] = s["opacity"] + oboost
+    cam = so.camera_c0(W, H) if camspec[0] == "c0" else so.camera_orbit(camspec[1], camspec[2], W, H)
+    bg_t = torch.tensor(bg)
+    o_out, o_grads, o_loss = util.oracle_render_with_grads(cam, s, bg_t)
+    c_out, c_grads, c_loss, rd, m = util.cuda_render_with_grads(cam, s, bg_t)
+    dbg = rd._last_debug
+    # index work: exact
+    assert torch.equal(c_out["visibility_filter"].cpu(), o_out["visibility_filter"])
+    assert torch.equal(c_out["radii"].detach().cpu().int(), o_out["radii"].detach().int())
+    assert np.array_equal(c_out["viewspace_points"].detach().cpu().numpy().view(np.uint32),
+                          o_out["viewspace_points"].detach().numpy().view(np.uint32))
+    assert torch.equal(dbg["entry_ids"].cpu().long(), o_out["sort_ids"])
+    assert torch.equal(dbg["tile_ranges"].cpu().long(), o_out["tile_ranges"])
+    assert torch.equal(dbg["n_consumed"].cpu().long(), o_out["n_consumed"])
+    assert torch.equal(dbg["tile_consumed"].cpu().long(), o_out["tile_consumed"])
+    # images and gradients
+    for k in ("image", "alpha", "depth"):
+        assert util.max_abs(c_out[k], o_out[k]) < IMG_TOL, k
+    for k in ("xyz", "scaling", "opacity", "features_dc", "means2D"):
+        assert util.rel_err(c_grads[k], o_grads[k]) < GRAD_TOL, k
+    if not util.is_isotropic(s["scaling"]):
+        assert util.rel_err(c_grads["rotation"], o_grads["rotation"]) < GRAD_TOL
+
+
+def test_sort_keys_bit_exact_vs_oracle():
+    """(tile_id<<32 | depth_bits) keys of every list entry, in order, equal the oracle's."""
+    import ctypes
+    from importlib import import_module
+    _lib = import_module("mini-3d-gaussian-splatting_b200._lib")
+    import gsplat_b200 as gb
+    s = so.scene_aniso(5000, 31)
+    s["scaling"] = s["scaling"] + math.log(2.0)
+    cam = so.camera_orbit(1, 5, 320, 200)
+    with torch.no_grad():
+        o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
+                                  torch.zeros(3), 200, 320)
+    m = util.cuda_model_from_params(s)
+    rd = gb.GaussianRenderer()
+    with torch.no_grad():
+        rd.render(util.cuda_camera(cam), m, gb.RenderSettings(200, 320, torch.zeros(3)))
+    dbg = rd._last_debug
+    D = dbg["entry_ids"].numel()
+    assert D == o["sort_ids"].numel()
+    tiles = torch.repeat_interleave(torch.arange(dbg["tile_ranges"].shape[0], device="cuda"),
+                                    (dbg["tile_ranges"][:, 1] - dbg["tile_ranges"][:, 0]).long())
+    keys = (tiles.long() << 32) | (dbg["depth_keys"][dbg["entry_ids"].long()].long() & 0xFFFFFFFF)
+    assert torch.equal(keys.cpu(), o["sort_keys"])
+    # and through the ABI's own key output
+    lib = _lib.load()
+    n = s["xyz"].shape[0]
+    num_tiles = dbg["tile_ranges"].shape[0]
+    counters = torch.empty(3, dtype=torch.int64, device="cuda")
+    sorted_ids = torch.empty(n, dtype=torch.int32, device="cuda")
+    offsets = torch.empty(n, dtype=torch.int64, device="cuda")
+    wsb = int(lib.gs_bin_workspace_bytes(n, D, num_tiles))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = _lib.ptr
+    _lib.check(lib.gs_bin_prepare(n, P(dbg["depth_keys"]), P(dbg["tiles_touched"]), P(ws), wsb, P(sorted_ids), P(offsets),
+                                  P(counters), st), "prepare")
+    ns, d2, nv = counters.tolist()
+    assert d2 == D
+    entry_ids = torch.empty(D, dtype=torch.int32, device="cuda")
+    ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device="cuda")
+    ekeys = torch.empty(D, dtype=torch.int64, device="cuda")
+    _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
+                               P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), st), "sort")
+    assert torch.equal(ekeys.cpu(), o["sort_keys"])
+    assert torch.equal(entry_ids.cpu().long(), o["sort_ids"])
+
+
+def test_all_invisible_returns_background_once_unclamped_and_zero_grads():
+    import gsplat_b200 as gb
+    s = so.scene_aniso(64, 3)
+    s["xyz"][:, 2] = -5.0 - s["xyz"][:, 2].abs()     # everything behind camera C0
+    m = util.cuda_model_from_params(s)
+    bg = torch.tensor([0.2, 1.5, -0.25])
+    out = gb.GaussianRenderer().render(gb.Camera.look_at_origin_c0(48, 32), m, gb.RenderSettings(32, 48, bg))
+    assert int(out["visibility_filter"].sum()) == 0
+    assert torch.equal(out["image"].cpu(), bg.view(3, 1, 1).repeat(1, 32, 48))
+    assert float(out["alpha"].abs().max()) == 0 and float(out["depth"].abs().max()) == 0
+    (out["image"].sum() + out["alpha"].sum() + out["depth"].sum()).backward()
+    assert float(m._xyz.grad.abs().max()) == 0 and float(m._opacity.grad.abs().max()) == 0
+
+
+def test_background_twice_and_empty_scene():
+    import gsplat_b200 as gb
+    rd = gb.GaussianRenderer()
+    bg = torch.tensor([0.2, 0.1, 0.3])
+    g = StubGaussians([[0.0, 0.0, 1.0]], [[0.001] * 3], [[0.0, 0.0, 0.0]], [0.5])
+    out = rd.render(StubCamera(32, 32), g, gb.RenderSettings(32, 32, bg))
+    assert torch.allclose(out["image"][:, 0, 0].cpu(), 2 * bg)          # renderer.py:273 + :359
+    m = gb.GaussianModel(device="cuda")                                  # N = 0
+    out = rd.render(StubCamera(32, 32), m, gb.RenderSettings(32, 32, bg))
+    assert torch.allclose(out["image"].cpu(), bg.view(3, 1, 1).expand(3, 32, 32))
+    assert out["viewspace_points"].shape == (0, 2)
+
+
+def test_determinism_forward_bitwise():
+    import gsplat_b200 as gb
+    s = so.scene_aniso(20000, 5)
+    s["scaling"] = s["scaling"] + math.log(1.5)
+    m = util.cuda_model_from_params(s)
+    rd = gb.GaussianRenderer()
+    cam = gb.Camera.orbit(3, 8, 640, 360)
+    st = gb.RenderSettings(360, 640, torch.tensor([0.1, 0.1, 0.1]))
+    with torch.no_grad():
+        a = rd.render(cam, m, st)
+        b = rd.render(cam, m, st)
+    for k in ("image", "alpha", "depth", "radii", "conics", "viewspace_points"):
+        assert torch.equal(a[k], b[k]), k
+
+
+# ----------------------------------------------------------------------------------------------
+# (4) BASELINE config[1] size: 1M splats, 1920x1080 -- properties + sampled tiles vs the oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_scene():
+    import gsplat_b200 as gb
+    m = gb.GaussianModel(device="cuda")
+    m.create_from_random(1_000_000, 1.0, seed=0)
+    rd = gb.GaussianRenderer()
+    W, H = 1920, 1080
+    cam = gb.Camera.look_at_origin_c0(W, H)
+    out = rd.render(cam, m, gb.RenderSettings(H, W, torch.zeros(3)))
+    return m, rd, out, W, H
+
+
+def test_full_size_binning_properties(full_scene):
+    m, rd, out, W, H = full_scene
+    dbg, stats = rd._last_debug, rd.last_stats
+    tiles_x, tiles_y = 120, 68
+    # survey-measured statistics of this exact scene: V = 937116, D = 26217475
+    assert stats["num_visible"] == 937116
+    assert stats["tile_pairs"] == 26217475
+    cnt = dbg["tiles_touched"].long()
+    assert int(cnt.sum()) == stats["tile_pairs"] and int(cnt.max()) <= 64
+    ranges = dbg["tile_ranges"].long()
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == stats["tile_pairs"]
+    assert torch.equal(ranges[1:, 0][lens[1:] > 0], torch.cumsum(lens, 0)[:-1][lens[1:] > 0])
+    # per-tile depth order: keys non-decreasing over the whole array
+    ids = dbg["entry_ids"].long()
+    tiles = torch.repeat_interleave(torch.arange(tiles_x * tiles_y, device="cuda"), lens)
+    keys = (tiles << 32) | (dbg["depth_keys"][ids].long() & 0xFFFFFFFF)
+    assert bool((keys[1:] >= keys[:-1]).all())
+    # ties keep ascending splat index (stable sort)
+    same = keys[1:] == keys[:-1]
+    assert bool((ids[1:][same] > ids[:-1][same]).all())
+    # every entry's tile lies inside its splat's rectangle
+    rect = dbg["tile_rect"].long() & 0xFFFF
+    r = rect[ids]
+    tx, ty = tiles % tiles_x, tiles // tiles_x
+    assert bool(((tx >= r[:, 0]) & (tx <= r[:, 2]) & (ty >= r[:, 1]) & (ty <= r[:, 3])).all())
+    # checksum of checksums: each splat appears exactly tiles_touched times
+    assert torch.equal(torch.bincount(ids, minlength=cnt.numel()), cnt)
+
+
+def test_full_size_image_properties(full_scene):
+    m, rd, out, W, H = full_scene
+    assert out["image"].shape == (3, H, W)
+    a = out["alpha"]
+    assert float(a.min()) >= 0 and float(a.max()) <= 1
+    assert bool(torch.isfinite(out["image"]).all()) and bool(torch.isfinite(out["depth"]).all())
+    dbg = rd._last_debug
+    ranges = dbg["tile_ranges"].long()
+    assert bool((dbg["tile_consumed"].long() <= (ranges[:, 1] - ranges[:, 0])).all())
+    # a pixel stops early only once saturated
+    ncons = dbg["n_consumed"].long()
+    lens_px = (ranges[:, 1] - ranges[:, 0]).view(68, 120).repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+    early = ncons < lens_px
+    assert bool((a[0][early] >= 0.995).all())
+    print(f"E (consumed entries, max per tile) = {int(dbg['tile_consumed'].sum())} of D = {rd.last_stats['tile_pairs']}; "
+          f"saturated pixels {float((a >= 0.995).float().mean()):.4f}")
+
+
+def test_full_size_sampled_tiles_vs_oracle_forward_and_backward(full_scene):
+    """Tiles sampled across the 1080p frame: forward values and, with the loss restricted to those
+    tiles, every parameter gradient against oracle autograd."""
+    m, rd, out, W, H = full_scene
+    dbg = rd._last_debug
+    tiles_x = 120
+    sample = [0, 59, 119, 120 * 34 + 60, 120 * 20 + 17, 120 * 50 + 101, 120 * 67, 120 * 67 + 119]
+    # oracle inputs = the CUDA projection outputs (projection parity is covered elsewhere), as leaves,
+    # compacted to the splats the sampled tiles list (autograd over 1M-row leaves would dominate)
+    cpu = lambda t: t.detach().cpu()  # noqa: E731
+    ranges_full = cpu(dbg["tile_ranges"]).long()
+    entry_ids = cpu(dbg["entry_ids"]).long()
+    per_tile = [entry_ids[int(ranges_full[t, 0]):int(ranges_full[t, 1])] for t in sample]
+    sub = torch.unique(torch.cat(per_tile))
+    ids_list, ranges, pos = [], torch.zeros_like(ranges_full), 0
+    for t, lst in zip(sample, per_tile):
+        ids_list += torch.searchsorted(sub, lst).tolist()
+        ranges[t, 0], ranges[t, 1] = pos, pos + lst.numel()
+        pos += lst.numel()
+    means2D = cpu(out["viewspace_points"])[sub].requires_grad_(True)
+    conics = cpu(out["conics"])[sub].requires_grad_(True)
+    depths = cpu(dbg["depths"])[sub].requires_grad_(True)
+    colors = torch.sigmoid(cpu(m._features_dc).reshape(-1, 3))[sub].requires_grad_(True)
+    opac = torch.sigmoid(cpu(m._opacity).reshape(-1))[sub].requires_grad_(True)
+    bg = torch.zeros(3)
+    wi, wa, wd = so.loss_weights(H, W)
+    g_img = torch.zeros(3, H, W); g_a = torch.zeros(1, H, W); g_d = torch.zeros(1, H, W)
+    loss = 0.0
+    qs = conics[:, 0, 1] + conics[:, 1, 0]
+    worst = {"image": 0.0, "alpha": 0.0, "depth": 0.0}
+    for tid in sample:
+        C, A, Ds, ncons, (y0, y1, x0, x1) = so.composite_tile(tid, ids_list, ranges, means2D, conics, qs, depths, colors,
+                                                             opac, bg, H, W)
+        rgb, al, dp = so.finish_pixels(C, A, Ds, bg)
+        hh, ww = y1 - y0, x1 - x0
+        worst["image"] = max(worst["image"], util.max_abs(out["image"][:, y0:y1, x0:x1], rgb.view(3, hh, ww)))
+        worst["alpha"] = max(worst["alpha"], util.max_abs(out["alpha"][0, y0:y1, x0:x1], al.view(hh, ww)))
+        worst["depth"] = max(worst["depth"], util.max_abs(out["depth"][0, y0:y1, x0:x1], dp.view(hh, ww)))
+        assert torch.equal(cpu(dbg["n_consumed"][y0:y1, x0:x1]).long(), ncons.view(hh, ww)), f"tile {tid}: termination differs"
+        loss = loss + (wi[:, y0:y1, x0:x1] * rgb.view(3, hh, ww)).sum() + (wa[0, y0:y1, x0:x1] * al.view(hh, ww)).sum() \
+            + 0.1 * (wd[0, y0:y1, x0:x1] * dp.view(hh, ww)).sum()
+        g_img[:, y0:y1, x0:x1] = wi[:, y0:y1, x0:x1]
+        g_a[:, y0:y1, x0:x1] = wa[:, y0:y1, x0:x1]
+        g_d[:, y0:y1, x0:x1] = 0.1 * wd[:, y0:y1, x0:x1]
+    for k, v in worst.items():
+        assert v < IMG_TOL, (k, v)
+    loss.backward()
+    # CUDA: same restricted loss through the product path; compare the rasteriser-level gradients
+    out["viewspace_points"].retain_grad()
+    out["conics"].retain_grad()
+    torch.autograd.backward([out["image"], out["alpha"], out["depth"]], [g_img.cuda(), g_a.cuda(), g_d.cuda()],
+                            retain_graph=True)
+    def scatter(g, shape):
+        full = torch.zeros(shape)
+        full[sub] = g
+        return full
+    n = m._xyz.shape[0]
+    assert util.rel_err(out["viewspace_points"].grad, scatter(means2D.grad, (n, 2))) < GRAD_TOL
+    assert util.rel_err(out["conics"].grad, scatter(conics.grad, (n, 2, 2))) < GRAD_TOL
+    # chain the oracle's rasteriser gradients through sigmoid to the parameters that depend on them only
+    g_dc = scatter(colors.grad * colors.detach() * (1 - colors.detach()), (n, 3)).view(-1, 1, 3)
+    g_op = scatter(opac.grad * opac.detach() * (1 - opac.detach()), (n,)).view(-1, 1)
+    assert util.rel_err(m._features_dc.grad, g_dc) < GRAD_TOL
+    assert util.rel_err(m._opacity.grad, g_op) < GRAD_TOL
+    for p in (m._xyz, m._scaling, m._rotation, m._opacity, m._features_dc, m._features_rest):
+        p.grad = None

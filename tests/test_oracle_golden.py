@@ -1,0 +1,129 @@
+"""CPU: the oracle restatement against fixtures produced by the literal reference
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU tests then compare the
+CUDA path with the oracle and with the same fixtures."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import splat_oracle as so
+from tests import util
+
+
+@pytest.mark.parametrize("name", util.RENDER_CASES)
+def test_oracle_matches_literal_reference_forward_and_grads(name):
+    if not util.golden_available(name):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(name)
+    cam = util.golden_camera(d)
+    out, grads, loss = util.oracle_render_with_grads(cam, util.golden_params(d), torch.tensor(d["bg"]))
+    # stage outputs: identical bits where the arithmetic is the same IEEE ops
+    assert np.array_equal(out["viewspace_points"].detach().numpy().view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert np.array_equal(out["depths"].detach().numpy().view(np.uint32), d["ref_depths"].view(np.uint32))
+    assert np.array_equal(out["visibility_filter"].numpy(), d["ref_vis"])
+    assert np.array_equal(out["radii"].detach().numpy().astype(np.int64), d["ref_radii"].astype(np.int64))
+    assert util.rel_err(out["conics"], torch.tensor(d["ref_conics"])) < 1e-6
+    assert torch.equal(so.sort_by_depth(out["visibility_filter"], out["depths"]), torch.tensor(d["ref_sorted_idx"]))
+    # images: BASELINE tolerance is 1e-4; the restatement is ~1e-7
+    assert util.max_abs(out["image"], torch.tensor(d["ref_image"])) < 2e-6
+    assert util.max_abs(out["alpha"], torch.tensor(d["ref_alpha"])) < 2e-6
+    assert util.max_abs(out["depth"], torch.tensor(d["ref_depth"])) < 2e-5
+    # gradients: tolerance 1e-3 relative; the restatement is ~1e-6
+    for k in ("xyz", "scaling", "opacity", "features_dc"):
+        assert util.rel_err(grads[k], torch.tensor(d["ref_g_" + k])) < 2e-5, k
+    assert util.rel_err(grads["means2D"], torch.tensor(d["ref_g_means2D"])) < 2e-5
+    g_rot_ref = torch.tensor(d["ref_g_rotation"])
+    if not util.is_isotropic(d["in_scaling"]):       # isotropic splats: rotation grads are pure rounding noise
+        assert util.rel_err(grads["rotation"], g_rot_ref) < 2e-5
+
+
+def test_oracle_known_answer_two_splats():
+    """The reference's own KAT (tests/test_renderer.py:127-161): alpha 0.75, depth 4/3."""
+    d = util.load_golden("kat_two_splats_64x64")
+    cam = util.golden_camera(d)
+    feats = torch.tensor(d["in_features"])
+    out = so.render(cam, torch.tensor(d["in_xyz"]), torch.tensor(d["in_cov3d"]), feats[:, 0, :],
+                    torch.tensor(d["in_opacity"]).reshape(-1), torch.tensor(d["bg"]), 64, 64)
+    assert abs(float(out["alpha"][0, 32, 32]) - 0.75) < 1e-3
+    exp_rgb = 0.5 * torch.sigmoid(torch.tensor([1.0, 0, 0])) + 0.25 * torch.sigmoid(torch.tensor([0, 1.0, 0]))
+    assert torch.allclose(out["image"][:, 32, 32], exp_rgb, atol=1e-3)
+    assert abs(float(out["depth"][0, 32, 32]) - 4 / 3) < 2e-2
+    assert util.max_abs(out["image"], torch.tensor(d["ref_image"])) < 1e-6
+    assert util.max_abs(out["alpha"], torch.tensor(d["ref_alpha"])) < 1e-6
+
+
+def test_oracle_all_behind_returns_background_once():
+    """renderer.py:74-83 and the reference's test_culling_all_behind."""
+    cam = so.OracleCamera(32, 32, math.radians(60), math.radians(60), torch.eye(4))
+    xyz = torch.tensor([[0.0, 0.0, -1.0], [0.0, 0.0, -2.0]])
+    cov = torch.diag_embed(torch.full((2, 3), 1e-4))
+    bg = torch.tensor([0.2, 0.3, 0.4])
+    out = so.render(cam, xyz, cov, torch.zeros(2, 3), torch.tensor([0.5, 0.5]), bg, 64, 64)
+    assert torch.allclose(out["image"], bg.view(3, 1, 1).expand(3, 64, 64))
+    assert int(torch.count_nonzero(out["alpha"])) == 0 and int(out["visibility_filter"].sum()) == 0
+
+
+def test_oracle_background_counted_twice_when_something_is_visible():
+    """renderer.py:273 + :359: an empty pixel shows 2*bg once any splat passed culling."""
+    cam = so.OracleCamera(32, 32, math.radians(60), math.radians(60), torch.eye(4))
+    xyz = torch.tensor([[0.0, 0.0, 1.0]])
+    cov = torch.diag_embed(torch.full((1, 3), 1e-6))
+    bg = torch.tensor([0.2, 0.1, 0.3])
+    out = so.render(cam, xyz, cov, torch.zeros(1, 3), torch.tensor([0.5]), bg, 32, 32)
+    assert torch.allclose(out["image"][:, 0, 0], 2 * bg)
+
+
+@pytest.mark.parametrize("tag", ["c0", "orbit5of16"])
+def test_oracle_stage_fixture_integer_outputs(tag):
+    """Stages 1-3 of the literal reference at 1080p on 200k anisotropic splats: pixel centres and
+    depths bit-equal, radii / visibility / tile rectangles exact."""
+    name = f"stages_aniso_n200000_1080p_{tag}"
+    if not util.golden_available(name):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(name)
+    n = int(d["n"])
+    s = so.scene_aniso(n, int(d["seed"]))
+    cam = util.golden_camera(d)
+    with torch.no_grad():
+        o = so.project(s["xyz"], so.covariance_3d(s["scaling"], s["rotation"]), cam)
+        vis = so.cull(o["means2D"], o["depths"], o["radii"], cam.height, cam.width)
+    assert np.array_equal(o["means2D"].numpy().view(np.uint32), d["ref_means2D_bits"])
+    assert np.array_equal(o["depths"].numpy().view(np.uint32), d["ref_depth_bits"])
+    assert np.array_equal(np.packbits(vis.numpy()), d["ref_vis"])
+    assert np.array_equal(o["radii"].numpy().astype(np.int32), d["ref_radii"].astype(np.int32))
+    cf = so.radii_closed_form(o["cov2D"])
+    assert np.array_equal(cf.numpy().astype(np.int32), d["ref_radii"].astype(np.int32))
+    assert util.rel_err(cf, torch.tensor(d["ref_radii"])) < 5e-7
+    tx0, tx1, ty0, ty1, cnt = so.tile_rects(o["means2D"], o["radii"], cam.height, cam.width)
+    rect = torch.stack([tx0, tx1, ty0, ty1], 1).numpy().astype(np.int16)
+    v = vis.numpy()
+    assert np.array_equal(rect[v], d["ref_rect"][v])
+    assert np.array_equal(cnt.numpy().astype(np.int16)[v], d["ref_cnt"][v])
+
+
+def test_bin_tiles_equals_append_loop():
+    """bin_tiles (flat arrays) against a direct transcription of the reference's append loop
+    semantics on a small scene: per-tile lists in global depth order."""
+    s = so.scene_aniso(300, 7)
+    s["scaling"] = s["scaling"] + math.log(6.0)
+    cam = so.camera_orbit(2, 9, 80, 56)
+    with torch.no_grad():
+        o = so.project(s["xyz"], so.covariance_3d(s["scaling"], s["rotation"]), cam)
+        vis = so.cull(o["means2D"], o["depths"], o["radii"], 56, 80)
+        ids = so.sort_by_depth(vis, o["depths"])
+        keys, flat, ranges = so.bin_tiles(ids, o["means2D"], o["radii"], o["depths"], 56, 80)
+    tiles_x, tiles_y = 5, 4
+    lists = [[] for _ in range(tiles_x * tiles_y)]
+    for i in ids.tolist():
+        r = int(o["radii"][i]); cx = int(o["means2D"][i, 0]); cy = int(o["means2D"][i, 1])
+        x0, x1 = max(cx - r, 0), min(cx + 1 + r, 80)
+        y0, y1 = max(cy - r, 0), min(cy + 1 + r, 56)
+        if x0 >= x1 or y0 >= y1:
+            continue
+        for ty in range(y0 // 16, (y1 - 1) // 16 + 1):
+            for tx in range(x0 // 16, (x1 - 1) // 16 + 1):
+                lists[ty * tiles_x + tx].append(i)
+    for t in range(tiles_x * tiles_y):
+        assert flat[int(ranges[t, 0]):int(ranges[t, 1])].tolist() == lists[t]
+    assert bool((keys[1:] >= keys[:-1]).all())

@@ -1,0 +1,92 @@
+"""Shared helpers for the test-suite: golden fixtures, scene builders, comparisons."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+import torch
+
+from oracle import splat_oracle as so
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PARAM_KEYS = ("xyz", "scaling", "rotation", "opacity", "features_dc")
+RENDER_CASES = ["aniso_n80_40x40_rot", "aniso_n120_48x40_orbit", "refinit_n300_64x64_saturating",
+                "aniso_n200_96x64_bigsplats"]
+
+
+def golden_available(name: str) -> bool:
+    return os.path.exists(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def load_golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def golden_camera(d) -> so.OracleCamera:
+    return so.OracleCamera(int(d["size_WH"][0]), int(d["size_WH"][1]), float(d["cam_fov"][0]), float(d["cam_fov"][1]),
+                           torch.tensor(d["cam_WV"], dtype=torch.float32))
+
+
+def golden_params(d):
+    return {k: torch.tensor(d["in_" + k]) for k in PARAM_KEYS}
+
+
+def is_isotropic(scaling) -> bool:
+    """All three log-scales equal for every splat: the covariance does not depend on the rotation,
+    so rotation gradients are rounding noise and are not compared."""
+    sc = np.asarray(scaling)
+    return bool(np.all(sc.max(axis=1) == sc.min(axis=1)))
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max|a-b| / max|b| -- the gradient metric of BASELINE.json's north_star."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def oracle_render_with_grads(cam: so.OracleCamera, params, bg, weights=None):
+    """Oracle forward + autograd backward with the SURVEY 8d fixed-weight loss."""
+    leaf = {k: params[k].clone().requires_grad_(True) for k in PARAM_KEYS}
+    H, W = cam.height, cam.width
+    out = so.render_from_params(cam, leaf["xyz"], leaf["scaling"], leaf["rotation"], leaf["opacity"], leaf["features_dc"],
+                                bg, H, W, return_stats=True)
+    out["viewspace_points"].retain_grad()
+    loss = so.weighted_loss(out, weights if weights is not None else so.loss_weights(H, W))
+    loss.backward()
+    grads = {k: leaf[k].grad for k in PARAM_KEYS}
+    grads["means2D"] = out["viewspace_points"].grad
+    return out, grads, loss.detach()
+
+
+def cuda_model_from_params(params, device="cuda"):
+    import gsplat_b200 as gb
+    m = gb.GaussianModel(device=device)
+    m.create_from_tensors(params["xyz"], params["features_dc"], params["scaling"], params["rotation"], params["opacity"],
+                          params.get("features_rest"))
+    return m
+
+
+def cuda_camera(cam: so.OracleCamera):
+    import gsplat_b200 as gb
+    return gb.Camera(cam.width, cam.height, cam.fovx, cam.fovy, world_view=cam.world_view)
+
+
+def cuda_render_with_grads(cam: so.OracleCamera, params, bg, weights=None, renderer=None):
+    import gsplat_b200 as gb
+    m = cuda_model_from_params(params)
+    H, W = cam.height, cam.width
+    rd = renderer or gb.GaussianRenderer()
+    out = rd.render(cuda_camera(cam), m, gb.RenderSettings(H, W, bg.cuda()))
+    out["viewspace_points"].retain_grad()
+    w = weights if weights is not None else so.loss_weights(H, W)
+    loss = so.weighted_loss(out, tuple(t.cuda() for t in w))
+    loss.backward()
+    grads = {"xyz": m._xyz.grad, "scaling": m._scaling.grad, "rotation": m._rotation.grad, "opacity": m._opacity.grad,
+             "features_dc": m._features_dc.grad, "features_rest": m._features_rest.grad,
+             "means2D": out["viewspace_points"].grad}
+    return out, grads, loss.detach(), rd, m
