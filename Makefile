@@ -4,7 +4,7 @@
 # `python -c "import __graft_entry__ as g; g.build()"` drives the same commands.
 
 NVCC      ?= nvcc
-CC        ?= gcc
+CC        := gcc
 PKG       := mini-3d-gaussian-splatting_b200
 CSRC      := $(PKG)/csrc
 LIBDIR    := $(PKG)/lib

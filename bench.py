@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd frames/s of the render hot path at BASELINE.json's config[1]
+(1 000 000 random-init Gaussians, 1920x1080, camera C0), one view per GPU per step.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference [...]      # the CPU port of the reference path (oracle/), host cores
+
+A step = one pass of the hot path over one view per rank: render forward (project -> depth sort ->
+tile binning -> compositing), the SURVEY 8d fixed-weight loss, backward (compositing and projection
+backward), and for N > 1 the gradient/statistics all-reduce.  Prints ONE JSON line (rank 0).
+
+  value      frames/s, whole job, inputs resident in HBM, timed on the device with CUDA events per
+             step (L2 flushed before every step, max over ranks)
+  e2e        frames/s through the public API with that step's host inputs (camera + loss weights,
+             pinned) copied H2D and the loss read back D2H inside the timed region
+  roofline   the dominant kernel (largest share of the step): algorithmic bytes / its CUDA-event
+             duration vs the measured HBM peak of MEASURED_PEAKS.json; `kernels` lists all stages
+  cpu_baseline  the oracle's plain-C port of the same path on the host cores (bounded sample)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_SPLATS = 1_000_000
+WIDTH, HEIGHT = 1920, 1080
+METRIC = "fwd+bwd frames/s at 1080p, 1M Gaussians"
+UNIT = "frames/s"
+WORKLOAD = "config[1]: 1M random-init Gaussians (create_from_random, CPU seed 0), 1920x1080, camera C0 / orbit views, fwd+bwd"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_frames_per_s(sample_tiles: int, repeats: int = 1):
+    """Times the C port on the bench workload: projection + culling + depth sort + tile binning at the
+    FULL size (1M splats), compositing forward+backward on a contiguous block of `sample_tiles` of the
+    8160 tiles from the middle of the frame, projection backward at full size.  frames/s is
+    1 / (t_full_stages + t_sampled_raster * 8160 / sample_tiles)."""
+    from oracle import c_port, splat_oracle as so
+    s = so.scene_ref_init(N_SPLATS, 0)
+    params = {k: s[k].numpy() for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
+    cam = so.camera_c0(WIDTH, HEIGHT)
+    cam16 = c_port.camera_block(cam.width, cam.height, cam.fovx, cam.fovy, cam.world_view.numpy())
+    wi, wa, wd = (t.numpy() for t in so.loss_weights(HEIGHT, WIDTH))
+    bg = np.zeros(3, np.float32)
+    tiles_total = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+    first = max(0, tiles_total // 2 - sample_tiles // 2)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        proj = c_port.project(cam16, WIDTH, HEIGHT, params["xyz"], params["scaling"], params["rotation"], None,
+                              params["opacity"], True, params["features_dc"].reshape(-1, 3))
+        sorted_ids, entry_ids, ranges = c_port.bin_tiles(proj, WIDTH, HEIGHT)
+        t1 = time.perf_counter()
+        c_port.raster_fwd(proj, entry_ids, ranges, bg, WIDTH, HEIGHT, first, sample_tiles)
+        g = c_port.raster_bwd(proj, entry_ids, ranges, bg, WIDTH, HEIGHT, wi, wa, 0.1 * wd, first, sample_tiles)
+        t2 = time.perf_counter()
+        c_port.project_bwd(proj, g)
+        t3 = time.perf_counter()
+        full = (t1 - t0) + (t3 - t2)
+        frame = full + (t2 - t1) * tiles_total / sample_tiles
+        if best is None or frame < best[0]:
+            best = (frame, full, t2 - t1)
+    frame, full, rast = best
+    return {"value": 1.0 / frame, "unit": UNIT, "cores": c_port.num_threads(), "kind": "port",
+            "sample": (f"C port of the reference path (oracle/splat_oracle.c, OpenMP): project+cull+sort+bin+project_bwd at full size "
+                       f"({full:.2f} s) + compositing fwd+bwd on {sample_tiles} of {tiles_total} tiles ({rast:.2f} s), extrapolated to the frame"),
+            "seconds_per_frame": frame}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    times = []
+    res = None
+    t_start = time.perf_counter()
+    for i in range(warm + steps):
+        res = cpu_port_frames_per_s(sample_tiles=args.cpu_sample_tiles)
+        if i >= warm:
+            times.append(res["seconds_per_frame"])
+        if times and time.perf_counter() - t_start > 150:        # bounded: the whole arm stays within minutes
+            break
+    sec = float(np.mean(times))
+    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["cpu_baseline"]["value"] = line["value"]
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-tiles", type=int, default=96)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--splats", type=int, default=N_SPLATS, help="debug only; the reported metric is defined at 1M")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import gsplat_b200 as gb
+    from importlib import import_module
+    mv = import_module("mini-3d-gaussian-splatting_b200.multiview")
+    rmod = import_module("mini-3d-gaussian-splatting_b200.renderer")
+    lib = import_module("mini-3d-gaussian-splatting_b200._lib").load()
+    from oracle import splat_oracle as so   # only for the seeded loss weights shared with the tests / CPU arm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n = args.splats
+
+    model = gb.GaussianModel(device=dev)
+    model.create_from_random(n, 1.0, seed=0)          # identical scene on every rank (replicated Gaussians)
+    rd = gb.GaussianRenderer()
+    settings = gb.RenderSettings(HEIGHT, WIDTH, torch.zeros(3, device=dev))
+    # one view per rank per step: rank r renders orbit view r of `world` (C0 when single-GPU)
+    cam = gb.Camera.look_at_origin_c0(WIDTH, HEIGHT) if world == 1 else gb.Camera.orbit(rank, world, WIDTH, HEIGHT)
+    w_host = [t.pin_memory() for t in so.loss_weights(HEIGHT, WIDTH)]
+    w_dev = [t.to(dev) for t in w_host]
+    buf = mv.FlatGradBuffer(model)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def loss_fn(out, w):
+        return (w[0] * out["image"]).sum() + (w[1] * out["alpha"]).sum() + 0.1 * (w[2] * out["depth"]).sum()
+
+    def step_device():
+        res = mv.multiview_step(model, rd, [cam], settings, lambda out, vid: loss_fn(out, w_dev), buffer=buf, reduce=world > 1)
+        return res["losses"][0]
+
+    cam_wv_host = cam.world_view_transform().clone().pin_memory()
+    stage = [torch.empty_like(t, device=dev) for t in w_host]
+
+    def step_e2e():
+        # this step's host inputs: camera pose + loss weights (the "ground truth" side of the step)
+        c = gb.Camera(WIDTH, HEIGHT, cam._FoVx, cam._FoVy, world_view=cam_wv_host)   # pose: 64 B, passed by value to the kernels
+        for s_, h_ in zip(stage, w_host):
+            s_.copy_(h_, non_blocking=True)
+        res = mv.multiview_step(model, rd, [c], settings, lambda out, vid: loss_fn(out, stage), buffer=buf, reduce=world > 1)
+        return float(res["losses"][0].item())                    # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    # ---- timed region (device-resident inputs) ------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.gs_kernel_launch_count()
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                   # L2 flush, outside the per-step event pair
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_device()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.gs_kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- e2e (host inputs, through the public API) --------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * e2e_steps / float(t.item())
+    h2d = sum(x.numel() * 4 for x in w_host) + 64
+    d2h = 4 + 24           # loss scalar + the (V, D, visible) counters of the frame
+
+    # ---- per-kernel events (extra, untimed steps) -> roofline -------------------------------------
+    timer = rmod.StageTimer()
+    rmod.stage_timer.active = timer
+    for _ in range(3):
+        flush.zero_()
+        step_device()
+    rmod.stage_timer.active = None
+    per = {k: float(np.mean(v)) for k, v in timer.summary_ms().items()}
+    st = rd.last_stats
+    V, D = st["num_visible"], st["tile_pairs"]
+    T = rd._last_debug["tile_ranges"].shape[0]
+    E = int(rd._last_debug["tile_consumed"].sum().item())
+    P = WIDTH * HEIGHT
+    # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
+    alg = {
+        "project_fwd": n * (56 + 109),                       # xyz 12+scale 12+quat 16+opacity 4+dc 12 ; outputs 109
+        "bin_prepare": n * (4 + 8 * 4 * 2 + 4 + 8 + 8),       # iota, 4 radix passes over (key,id), gather, scan
+        "bin_sort": n * 28 + D * 8 + D * (4 + 2 * 16) + D * 4 + T * 8,   # duplicate, 2 radix passes of (key,id) + histogram, ranges
+        "raster_fwd": T * 12 + E * 52 + P * 40,
+        "raster_bwd": T * 12 + E * 52 + E * 44 + P * 40,
+        "project_bwd": n * (56 + 44 + 56),
+    }
+    hbm_peak, peak_src = measured_peaks()
+    kernels = {k: {"ms": per[k], "alg_bytes": alg[k], "gbs": alg[k] / (per[k] * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": alg[k] / (per[k] * 1e-3) / 1e9 / hbm_peak, "share_of_step": per[k] / ms_per_step}
+               for k in per if k in alg}
+    top = max(kernels, key=lambda k: kernels[k]["ms"])
+    evals = None
+    if top in ("raster_fwd", "raster_bwd"):
+        ncons = rd._last_debug["n_consumed"]
+        evals = float(ncons.sum().item())      # pixel x list-entry evaluations actually walked
+    roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[top]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                "note": ("the compositing kernels are FP32/MUFU-issue bound, not HBM bound (SURVEY 8d): see `issue`"
+                         if evals else "")}
+    if evals:
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        lane_roof = 148 * 128 * sm_clock * 1e6
+        roofline["issue"] = {"pixel_splat_evals": evals, "evals_per_s": evals / (kernels[top]["ms"] * 1e-3),
+                             "fp32_lane_instr_per_s_roof": lane_roof,
+                             "lane_instr_per_eval_at_roof": lane_roof / (evals / (kernels[top]["ms"] * 1e-3))}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_port_frames_per_s(args.cpu_sample_tiles)
+                cpu.pop("seconds_per_frame", None)
+            except Exception as e:   # the GPU number must not be lost to a host-side problem
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_gpu_per_step": 1, "splats": n, "resolution": [WIDTH, HEIGHT],
+                       "visible": V, "tile_pairs_D": D, "consumed_entries_E": E,
+                       "l2": "flushed before every timed step (256 MiB memset); per-step working set > L2",
+                       "parallelism": f"view-sharded dp{world}, replicated Gaussians, NCCL allreduce of 16N floats" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kernels,
+            "wall_frames_per_s": world * args.steps / t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

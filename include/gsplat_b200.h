@@ -59,6 +59,9 @@ int gs_abi_version(void);
 const char* gs_last_error_string(void);
 /* Compute capability the kernels were built for (100 for sm_100a). */
 int gs_built_for_sm(void);
+/* Cumulative number of hand-written kernels this process has launched through the entry points
+ * below (CUB's internal sort/scan kernels are not counted).  Statistics only. */
+int64_t gs_kernel_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Stage P+M+C: projection, fused with activations, 3-D covariance and frustum culling.

@@ -19,6 +19,7 @@ SIGNATURES = {
     "gs_abi_version": (c_int32, []),
     "gs_last_error_string": (c_char_p, []),
     "gs_built_for_sm": (c_int32, []),
+    "gs_kernel_launch_count": (c_int64, []),
     "gs_project_fwd": (c_int32, [c_int64, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P,
                                   c_int32, c_int32, c_int32, c_float, c_float,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

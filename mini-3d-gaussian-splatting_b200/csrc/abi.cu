@@ -3,6 +3,8 @@
 
 #include <stdarg.h>
 
+#include <atomic>
+
 namespace gs {
 
 static thread_local char g_error[512] = "";
@@ -14,6 +16,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return GS_ERR_CUDA;
@@ -24,6 +30,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
 
 extern "C" const char* gs_last_error_string(void) { return gs::g_error; }
+
+namespace gs { long long launches(); }
+extern "C" int64_t gs_kernel_launch_count(void) { return (int64_t)gs::launches(); }
 
 extern "C" int gs_built_for_sm(void) {
 #ifdef GS_BUILT_FOR_SM

@@ -208,6 +208,7 @@ extern "C" int gs_bin_prepare(int64_t n, const uint32_t* depth_keys, const int32
     GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, it, offsets, n, st));
     counters_kernel<<<1, 32, 0, st>>>(n, keys_sorted, sorted_ids, tiles_touched, offsets, counters);
     GS_CUDA_TRY(cudaGetLastError());
+    count_launches(2);   // iota + counters
     return GS_OK;
 }
 
@@ -249,9 +250,11 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     const unsigned blocks_d = (unsigned)((d + threads - 1) / threads);
     ranges_kernel<<<blocks_d, threads, 0, st>>>(d, keys_out, tile_ranges);
     GS_CUDA_TRY(cudaGetLastError());
+    count_launches(2);   // duplicate + ranges
     if (entry_keys) {
         entry_keys_kernel<<<blocks_d, threads, 0, st>>>(d, keys_out, entry_ids, depth_keys, entry_keys);
         GS_CUDA_TRY(cudaGetLastError());
+        count_launches(1);
     }
     return GS_OK;
 }

@@ -11,6 +11,8 @@ namespace gs {
 
 // ---- error plumbing: thread-local message, int status across the C ABI -------------------
 void set_error(const char* fmt, ...);
+// statistics only (relaxed atomic): hand-written kernels launched by this process
+void count_launches(int n);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define GS_CUDA_TRY(expr)                                   \

@@ -400,9 +400,9 @@ extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_
         return GS_ERR_UNSUPPORTED;
     }
     GS_REQUIRE((img_w + kTile - 1) / kTile <= 65535 && (img_h + kTile - 1) / kTile <= 65535, "image too large for uint16 tile rects");
+    if (n == 0) return GS_OK;
     const bool param_mode = scaling_log != nullptr && rotation != nullptr;
     GS_REQUIRE(param_mode || cov3d != nullptr, "need (scaling_log, rotation) or cov3d");
-    if (n == 0) return GS_OK;
     GS_REQUIRE(xyz && opacity && feat0 && means2d && depths && conics && radii && colors && opacities && vis &&
                    tiles_touched && tile_rect && depth_keys && splat_rec, "NULL array argument");
     DeviceGuard guard(xyz);
@@ -422,6 +422,7 @@ extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_
             tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec);
     }
     GS_CUDA_TRY(cudaGetLastError());
+    count_launches(1);
     return GS_OK;
 }
 
@@ -434,11 +435,11 @@ extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_
                               int64_t g_feat_stride, void* stream) {
     GS_REQUIRE(n >= 0, "n < 0");
     GS_REQUIRE(camera_host != nullptr, "camera_host is NULL");
+    if (n == 0) return GS_OK;
     const bool param_mode = scaling_log != nullptr && rotation != nullptr;
     GS_REQUIRE(param_mode || cov3d != nullptr, "need (scaling_log, rotation) or cov3d");
     GS_REQUIRE(!param_mode || (g_scaling_log && g_rotation), "parameter mode needs g_scaling_log and g_rotation");
     GS_REQUIRE(param_mode || g_cov3d, "covariance mode needs g_cov3d");
-    if (n == 0) return GS_OK;
     GS_REQUIRE(xyz && opacity && feat0 && g_means2d && g_conics && g_depths && g_colors && g_opacities && g_xyz &&
                    g_opacity && g_feat0, "NULL array argument");
     DeviceGuard guard(xyz);
@@ -458,5 +459,6 @@ extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_
             g_cov3d, g_opacity, g_feat0, g_feat_stride);
     }
     GS_CUDA_TRY(cudaGetLastError());
+    count_launches(1);
     return GS_OK;
 }

@@ -324,6 +324,7 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
         img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
         image, alpha, depth, (float4*)pix_state, n_consumed, tile_consumed);
     GS_CUDA_TRY(cudaGetLastError());
+    count_launches(1);
     return GS_OK;
 }
 
@@ -344,5 +345,6 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
         (const float4*)pix_state, tile_consumed, g_image, g_alpha, g_depth, g_means2d, g_conics, g_depths, g_colors,
         g_opacities);
     GS_CUDA_TRY(cudaGetLastError());
+    count_launches(1);
     return GS_OK;
 }

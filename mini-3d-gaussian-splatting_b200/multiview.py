@@ -1,0 +1,96 @@
+"""Multi-view step: views sharded over ranks, Gaussians replicated, one gradient/statistics
+reduction per step.
+
+The reference has no multi-GPU code; this is the caller the render path gets when a batch of
+cameras is split over the GPUs of one box.  Each rank renders its views through the ordinary
+single-GPU pipeline.  Parameter gradients accumulate -- through autograd's in-place
+accumulation -- directly into views of ONE flat fp32 buffer laid out as
+
+    [ xyz 3N | features_dc 3N | scaling 3N | rotation 4N | opacity N | grad-norm sum N | visible count N ]
+
+so the exchange is a single SUM all-reduce (64 B/splat) plus a MAX all-reduce of the screen
+radii, with no packing kernel.  Works with any torch.distributed backend: NCCL over NVLink on the
+GPUs, gloo in the CPU tests (where a stand-in renderer supplies the per-view outputs).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+PARAM_ORDER = ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity")
+
+
+def shard_views(num_views: int, rank: int, world_size: int) -> List[int]:
+    """Contiguous block partition of view indices; the first `num_views % world_size` ranks take one extra."""
+    base, extra = divmod(num_views, world_size)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+class FlatGradBuffer:
+    """One flat fp32 buffer whose slices are installed as the parameters' `.grad`."""
+
+    def __init__(self, model):
+        self.model = model
+        params = [getattr(model, name) for name in PARAM_ORDER]
+        n = params[0].shape[0]
+        sizes = [p.numel() for p in params]
+        self.n = n
+        self.param_elems = sum(sizes)
+        self.flat = torch.zeros(self.param_elems + 2 * n, dtype=torch.float32, device=params[0].device)
+        self.views = []
+        off = 0
+        for p, sz in zip(params, sizes):
+            self.views.append(self.flat[off:off + sz].view_as(p))
+            off += sz
+        self.grad_norm_sum = self.flat[off:off + n]
+        self.vis_count = self.flat[off + n:off + 2 * n]
+        self.max_radii = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+
+    def install(self) -> None:
+        self.flat.zero_()
+        self.max_radii.zero_()
+        for name, v in zip(PARAM_ORDER, self.views):
+            getattr(self.model, name).grad = v
+        rest = getattr(self.model, "_features_rest", None)
+        if rest is not None:
+            rest.grad = None           # DC-only colour: identically zero, never exchanged
+
+    def add_view_stats(self, viewspace_grad: torch.Tensor, visibility: torch.Tensor, radii: torch.Tensor) -> None:
+        vis_f = visibility.to(torch.float32)
+        self.grad_norm_sum += viewspace_grad.norm(dim=-1) * vis_f
+        self.vis_count += vis_f
+        torch.maximum(self.max_radii, radii * vis_f, out=self.max_radii)
+
+    def all_reduce(self, group=None) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
+
+
+def multiview_step(model, renderer, cameras: Sequence, settings, loss_fn: Callable[[Dict[str, torch.Tensor], int], torch.Tensor],
+                   view_ids: Optional[Sequence[int]] = None, buffer: Optional[FlatGradBuffer] = None,
+                   group=None, reduce: bool = True) -> Dict[str, object]:
+    """Render this rank's views, back-propagate `loss_fn(out, view_id)` for each, reduce.
+
+    After the call every rank holds, in `model.<param>.grad`, the sum over ALL views of all ranks,
+    and in `buffer.grad_norm_sum / vis_count / max_radii` the densification statistics the
+    reference allocates but never fills (gaussian_model.py:29-31).
+    """
+    buf = buffer if buffer is not None else FlatGradBuffer(model)
+    buf.install()
+    ids = list(view_ids) if view_ids is not None else list(range(len(cameras)))
+    losses = []
+    for cam, vid in zip(cameras, ids):
+        out = renderer.render(cam, model, settings)
+        out["viewspace_points"].retain_grad()
+        loss = loss_fn(out, vid)
+        loss.backward()
+        with torch.no_grad():
+            buf.add_view_stats(out["viewspace_points"].grad, out["visibility_filter"], out["radii"].detach())
+        losses.append(loss.detach())
+    if reduce:
+        buf.all_reduce(group)
+    return {"buffer": buf, "losses": losses}

@@ -67,6 +67,46 @@ def _stream(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class StageTimer:
+    """Optional CUDA-event timing of each ABI call, on the stream the kernels are launched on.
+    Assign an instance to ``stage_timer.active`` (module level) to collect; bench.py does, tests
+    and normal use leave it None so no events are recorded."""
+
+    def __init__(self):
+        self.events = []          # (name, start_event, end_event)
+
+    def summary_ms(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+class _TimerSlot:
+    active: Optional[StageTimer] = None
+
+
+stage_timer = _TimerSlot()
+
+
+class _timed:
+    def __init__(self, name, device):
+        self.name, self.device, self.t = name, device, stage_timer.active
+
+    def __enter__(self):
+        if self.t is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record(torch.cuda.current_stream(self.device))
+            self.t.events.append((self.name, self.a, b))
+        return False
+
+
 class _ProjectFn(torch.autograd.Function):
     """Stage P+M+C (gs_project_fwd / gs_project_bwd)."""
 
@@ -83,11 +123,12 @@ class _ProjectFn(torch.autograd.Function):
         tile_rect = new(n, 4, dtype=torch.int16)
         depth_keys = new(n, dtype=_I32)
         rec = new(n, 12)
-        check(lib.gs_project_fwd(
-            n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
-            ptr(feat_src), meta.feat_stride, meta.cam, meta.W, meta.H, meta.tile, meta.rmin, meta.rmax,
-            ptr(means2d), ptr(depths), ptr(conics), ptr(radii), ptr(colors), ptr(opac), ptr(vis),
-            ptr(tiles_touched), ptr(tile_rect), ptr(depth_keys), ptr(rec), _stream(dev)), "gs_project_fwd")
+        with _timed("project_fwd", dev):
+            check(lib.gs_project_fwd(
+                n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
+                ptr(feat_src), meta.feat_stride, meta.cam, meta.W, meta.H, meta.tile, meta.rmin, meta.rmax,
+                ptr(means2d), ptr(depths), ptr(conics), ptr(radii), ptr(colors), ptr(opac), ptr(vis),
+                ptr(tiles_touched), ptr(tile_rect), ptr(depth_keys), ptr(rec), _stream(dev)), "gs_project_fwd")
         ctx.meta = meta
         ctx.save_for_backward(xyz, scaling, rotation, cov3d, opacity, feat_src, features_rest)
         vis_b = vis.view(torch.bool)
@@ -123,12 +164,13 @@ class _ProjectFn(torch.autograd.Function):
             g_feat = torch.empty_like(feat_src)
         else:
             g_feat = torch.zeros_like(feat_src)
-        check(lib.gs_project_bwd(
-            n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
-            ptr(feat_src), meta.feat_stride, meta.cam,
-            ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
-            ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), ptr(g_cov3d), ptr(g_opacity),
-            ptr(g_feat), g_feat.stride(0), _stream(dev)), "gs_project_bwd")
+        with _timed("project_bwd", dev):
+            check(lib.gs_project_bwd(
+                n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
+                ptr(feat_src), meta.feat_stride, meta.cam,
+                ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
+                ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), ptr(g_cov3d), ptr(g_opacity),
+                ptr(g_feat), g_feat.stride(0), _stream(dev)), "gs_project_bwd")
         g_rest = torch.zeros_like(features_rest) if (features_rest is not None and ctx.needs_input_grad[7]) else None
         return None, g_xyz, g_scaling, g_rotation, g_cov3d, g_opacity, g_feat, g_rest
 
@@ -149,9 +191,10 @@ class _RasterizeFn(torch.autograd.Function):
         pix_state = torch.empty((H * W, 4), dtype=_F32, device=dev)
         n_consumed = torch.empty((H, W), dtype=_I32, device=dev)
         tile_consumed = torch.empty((tiles,), dtype=_I32, device=dev)
-        check(lib.gs_raster_fwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), int(any_visible),
-                                ptr(image), ptr(alpha), ptr(depth), ptr(pix_state), ptr(n_consumed),
-                                ptr(tile_consumed), _stream(dev)), "gs_raster_fwd")
+        with _timed("raster_fwd", dev):
+            check(lib.gs_raster_fwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
+                                    int(any_visible), ptr(image), ptr(alpha), ptr(depth), ptr(pix_state),
+                                    ptr(n_consumed), ptr(tile_consumed), _stream(dev)), "gs_raster_fwd")
         ctx.meta = meta
         ctx.any_visible = any_visible
         ctx.n = means2d.shape[0]
@@ -180,11 +223,12 @@ class _RasterizeFn(torch.autograd.Function):
                     return torch.zeros((c, H, W), dtype=_F32, device=dev)
                 return g.contiguous()
 
-            check(lib.gs_raster_bwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), ptr(alpha),
-                                    ptr(pix_state), ptr(n_consumed), ptr(tile_consumed),
-                                    ptr(dense(g_image, 3)), ptr(dense(g_alpha, 1)), ptr(dense(g_depth, 1)),
-                                    ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
-                                    _stream(dev)), "gs_raster_bwd")
+            gi, ga, gd = dense(g_image, 3), dense(g_alpha, 1), dense(g_depth, 1)
+            with _timed("raster_bwd", dev):
+                check(lib.gs_raster_bwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), ptr(alpha),
+                                        ptr(pix_state), ptr(n_consumed), ptr(tile_consumed), ptr(gi), ptr(ga), ptr(gd),
+                                        ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
+                                        _stream(dev)), "gs_raster_bwd")
         return None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None, None, None
 
 
@@ -286,8 +330,9 @@ class GaussianRenderer:
         offsets = torch.empty(n, dtype=_I64, device=device)
         ws_bytes = int(lib.gs_bin_workspace_bytes(n, 0, num_tiles))
         ws = torch.empty(ws_bytes, dtype=_U8, device=device)
-        check(lib.gs_bin_prepare(n, ptr(depth_keys), ptr(tiles_touched), ptr(ws), ws_bytes, ptr(sorted_ids),
-                                 ptr(offsets), ptr(counters), stream), "gs_bin_prepare")
+        with _timed("bin_prepare", device):
+            check(lib.gs_bin_prepare(n, ptr(depth_keys), ptr(tiles_touched), ptr(ws), ws_bytes, ptr(sorted_ids),
+                                     ptr(offsets), ptr(counters), stream), "gs_bin_prepare")
         # the one host sync of the frame (the reference syncs on vis_mask.sum() at renderer.py:74)
         num_sorted, D, num_vis = (int(v) for v in counters.tolist())
         tile_ranges = torch.empty((num_tiles, 2), dtype=_I32, device=device)
@@ -295,9 +340,10 @@ class GaussianRenderer:
         ws_bytes = int(lib.gs_bin_workspace_bytes(0, D, num_tiles))
         if ws.numel() < ws_bytes:
             ws = torch.empty(ws_bytes, dtype=_U8, device=device)
-        check(lib.gs_bin_sort(n, num_sorted, D, ptr(sorted_ids), ptr(offsets), ptr(tile_rect), ptr(depth_keys),
-                              tiles_x, num_tiles, ptr(ws), ws.numel(), ptr(entry_ids), ptr(tile_ranges), None,
-                              stream), "gs_bin_sort")
+        with _timed("bin_sort", device):
+            check(lib.gs_bin_sort(n, num_sorted, D, ptr(sorted_ids), ptr(offsets), ptr(tile_rect), ptr(depth_keys),
+                                  tiles_x, num_tiles, ptr(ws), ws.numel(), ptr(entry_ids), ptr(tile_ranges), None,
+                                  stream), "gs_bin_sort")
         entry_ids = entry_ids[:D]
 
         # ---- stage R -----------------------------------------------------------------------

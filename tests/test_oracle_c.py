@@ -1,0 +1,61 @@
+"""CPU: the plain-C port (oracle/splat_oracle.c) against the torch oracle (itself pinned to the literal
+reference) and against the literal-reference fixtures -- forward, bins and every gradient."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_port, splat_oracle as so
+from tests import util
+
+
+def _c_render(cam, params, bg):
+    cam16 = c_port.camera_block(cam.width, cam.height, cam.fovx, cam.fovy, cam.world_view.numpy())
+    p = {k: v.numpy() for k, v in params.items() if isinstance(v, torch.Tensor)}
+    w = tuple(t.numpy() for t in so.loss_weights(cam.height, cam.width))
+    return c_port.render_fwd_bwd(cam16, cam.width, cam.height, p, np.asarray(bg, np.float32), w)
+
+
+@pytest.mark.parametrize("name", ["aniso_n80_40x40_rot", "refinit_n300_64x64_saturating", "aniso_n200_96x64_bigsplats"])
+def test_c_port_matches_literal_reference_fixture(name):
+    if not util.golden_available(name):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(name)
+    cam = util.golden_camera(d)
+    res = _c_render(cam, util.golden_params(d), d["bg"])
+    pr = res["proj"]
+    assert np.array_equal(pr["means2D"].view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert np.array_equal(pr["depths"].view(np.uint32), d["ref_depths"].view(np.uint32))
+    assert np.array_equal(pr["vis"].astype(bool), d["ref_vis"])
+    assert np.array_equal(pr["radii"].astype(np.int64), d["ref_radii"].astype(np.int64))
+    assert np.array_equal(res["sorted_ids"].astype(np.int64), d["ref_sorted_idx"])
+    for k in ("image", "alpha", "depth"):
+        assert np.abs(res[k] - d["ref_" + k]).max() < 1e-5, k
+    g = res["grads"]
+    pairs = [("xyz", g["xyz"]), ("scaling", g["scaling"]), ("opacity", g["opacity"].reshape(-1, 1)),
+             ("features_dc", g["feat0"].reshape(-1, 1, 3)), ("means2D", res["g_raster"]["means2D"])]
+    if not util.is_isotropic(d["in_scaling"]):
+        pairs.append(("rotation", g["rotation"]))
+    for k, got in pairs:
+        assert util.rel_err(torch.tensor(got), torch.tensor(d["ref_g_" + k])) < 1e-4, k
+
+
+def test_c_port_matches_torch_oracle_midsize():
+    s = so.scene_aniso(1500, 41)
+    s["scaling"] = s["scaling"] + math.log(3.0)
+    s["opacity"] = s["opacity"] + 1.0
+    cam = so.camera_orbit(4, 9, 112, 80)
+    bg = torch.tensor([0.3, 0.2, 0.1])
+    o_out, o_grads, _ = util.oracle_render_with_grads(cam, s, bg)
+    res = _c_render(cam, s, bg.numpy())
+    assert np.array_equal(res["entry_ids"].astype(np.int64), o_out["sort_ids"].numpy())
+    util.assert_same_ranges(torch.tensor(res["ranges"]), o_out["tile_ranges"])
+    assert np.array_equal(res["n_consumed"].astype(np.int64), o_out["n_consumed"].numpy())
+    for k in ("image", "alpha", "depth"):
+        assert util.max_abs(torch.tensor(res[k]), o_out[k]) < 1e-5, k
+    g = res["grads"]
+    for k, got in [("xyz", g["xyz"]), ("scaling", g["scaling"]), ("rotation", g["rotation"]),
+                   ("opacity", g["opacity"].reshape(-1, 1)), ("features_dc", g["feat0"].reshape(-1, 1, 3)),
+                   ("means2D", res["g_raster"]["means2D"])]:
+        assert util.rel_err(torch.tensor(got), o_grads[k]) < 1e-4, k

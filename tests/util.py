@@ -90,3 +90,12 @@ def cuda_render_with_grads(cam: so.OracleCamera, params, bg, weights=None, rende
              "features_dc": m._features_dc.grad, "features_rest": m._features_rest.grad,
              "means2D": out["viewspace_points"].grad}
     return out, grads, loss.detach(), rd, m
+
+
+def assert_same_ranges(got: torch.Tensor, want: torch.Tensor) -> None:
+    """[begin,end) per tile: lengths equal everywhere, positions equal for non-empty tiles (an
+    empty tile's begin is unspecified: the kernel leaves (0,0), a cumulative sum leaves (k,k))."""
+    got, want = got.cpu().long(), want.cpu().long()
+    assert torch.equal(got[:, 1] - got[:, 0], want[:, 1] - want[:, 0])
+    nz = (want[:, 1] - want[:, 0]) > 0
+    assert torch.equal(got[nz], want[nz])
