@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -253,7 +253,6 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.gs_kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,6 +274,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * e2e_steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None      # sampled every 20 ms over the timed region and the e2e region
     h2d = sum(x.numel() * 4 for x in w_host) + 64
     d2h = 4 + 24           # loss scalar + the (V, D, visible) counters of the frame
 
