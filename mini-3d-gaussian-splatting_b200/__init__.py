@@ -8,3 +8,4 @@ from .renderer import GaussianRenderer, RenderSettings  # noqa: F401
 from .scene import Camera, GaussianModel  # noqa: F401
 
 __all__ = ["GaussianRenderer", "RenderSettings", "GaussianModel", "Camera"]
+from . import multiview  # noqa: F401,E402
