@@ -307,6 +307,8 @@ def main():
     top = max(kernels, key=lambda k: kernels[k]["ms"])
     evals = None
     if top in ("raster_fwd", "raster_bwd"):
+        with torch.no_grad():                   # one untimed debug render: per-pixel walk lengths
+            rd.render(cam, model, gb.RenderSettings(HEIGHT, WIDTH, torch.zeros(3, device=dev), debug=True))
         ncons = rd._last_debug["n_consumed"]
         evals = float(ncons.sum().item())      # pixel x list-entry evaluations actually walked
     roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 3
+#define GS_ABI_VERSION 4
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -52,7 +52,8 @@ typedef enum GsStatus {
 #define GS_CAMERA_FLOATS 16
 
 /* Per-splat record consumed by the raster kernels: 12 floats = 3 x float4, 48-byte stride.
- *   {mx, my, Q00, Q01+Q10} {Q11, opacity, depth, r} {g, b, 0, 0} */
+ *   {mx, my, c*Q00, c*(Q01+Q10)} {c*Q11, opacity, depth, r} {g, b, 0, 0},  c = -0.5*log2(e):
+ * the splat weight exp(-0.5*s) of renderer.py:333-334 is then one exp2 of the quadratic form. */
 #define GS_SPLAT_REC_FLOATS 12
 
 int gs_abi_version(void);
@@ -159,8 +160,11 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
  * culling: the reference returns the background ONCE, unclamped, when nothing is visible
  * (renderer.py:74-83) and adds it TWICE otherwise (renderer.py:273 + :359).
  * Outputs: image [3,H,W], alpha [1,H,W], depth [1,H,W];
- *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue,
- *   n_consumed [H*W] int32 = list entries the pixel walked, tile_consumed [num_tiles] int32 = max of it.
+ *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue;
+ *   tile_consumed [num_tiles] int32 = list entries the tile loaded before all its pixels saturated
+ *   (granularity: batches of 32); n_consumed [H*W] int32 (optional, may be NULL) = entries each
+ *   pixel walked up to and including the one that terminated it -- a debug/parity output that
+ *   selects a kernel variant with one extra predicated move per evaluation.
  * ------------------------------------------------------------------------------------- */
 int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
@@ -176,7 +180,7 @@ int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
                   const float* splat_rec, const float* bg,
                   const float* alpha, const float* pix_state,
-                  const int32_t* n_consumed, const int32_t* tile_consumed,
+                  const int32_t* tile_consumed,
                   const float* g_image, const float* g_alpha, const float* g_depth,
                   float* g_means2d, float* g_conics, float* g_depths,
                   float* g_colors, float* g_opacities,

@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LIB_NAME = "libgsplat_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
@@ -32,7 +32,7 @@ SIGNATURES = {
                                _P, c_int64, _P, _P, _P, _P]),
     "gs_raster_fwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32,
                                  _P, _P, _P, _P, _P, _P, _P]),
-    "gs_raster_bwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P,
+    "gs_raster_bwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -203,8 +203,10 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     tile_rect[i] = rect;
     // valid depths are < 0x7F800001, so the two sentinels sort behind every binned splat
     depth_keys[i] = cnt > 0 ? __float_as_uint(p.Z) : (vis ? 0xFFFFFFFEu : 0xFFFFFFFFu);
-    rec[i * 3 + 0] = make_float4(p.mx, p.my, p.q00, add_rn(p.q01, p.q10));
-    rec[i * 3 + 1] = make_float4(p.q11, op, p.Z, cr);
+    // raster record: conic pre-scaled by c = -0.5*log2(e) so that exp(-0.5*s) = exp2(quadratic form)
+    const float kC = -0.72134752044448170f;
+    rec[i * 3 + 0] = make_float4(p.mx, p.my, kC * p.q00, kC * add_rn(p.q01, p.q10));
+    rec[i * 3 + 1] = make_float4(kC * p.q11, op, p.Z, cr);
     rec[i * 3 + 2] = make_float4(cg, cb, 0.f, 0.f);
 }
 

@@ -180,7 +180,7 @@ class _RasterizeFn(torch.autograd.Function):
     ``viewspace_points``; its ``.grad`` after ``retain_grad()`` is what this backward emits."""
 
     @staticmethod
-    def forward(ctx, meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, any_visible):
+    def forward(ctx, meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, any_visible, track):
         lib = _lib.load()
         dev = means2d.device
         H, W = meta.H, meta.W
@@ -189,7 +189,8 @@ class _RasterizeFn(torch.autograd.Function):
         alpha = torch.empty((1, H, W), dtype=_F32, device=dev)
         depth = torch.empty((1, H, W), dtype=_F32, device=dev)
         pix_state = torch.empty((H * W, 4), dtype=_F32, device=dev)
-        n_consumed = torch.empty((H, W), dtype=_I32, device=dev)
+        # per-pixel consumed-entry counts: debug / parity output only (RenderSettings.debug)
+        n_consumed = torch.empty((H, W), dtype=_I32, device=dev) if track else None
         tile_consumed = torch.empty((tiles,), dtype=_I32, device=dev)
         with _timed("raster_fwd", dev):
             check(lib.gs_raster_fwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
@@ -198,7 +199,9 @@ class _RasterizeFn(torch.autograd.Function):
         ctx.meta = meta
         ctx.any_visible = any_visible
         ctx.n = means2d.shape[0]
-        ctx.save_for_backward(rec, entry_ids, tile_ranges, bg, alpha, pix_state, n_consumed, tile_consumed)
+        ctx.save_for_backward(rec, entry_ids, tile_ranges, bg, alpha, pix_state, tile_consumed)
+        if n_consumed is None:
+            n_consumed = torch.empty(0, dtype=_I32, device=dev)
         ctx.mark_non_differentiable(n_consumed, tile_consumed)
         return image, alpha, depth, n_consumed, tile_consumed
 
@@ -206,7 +209,7 @@ class _RasterizeFn(torch.autograd.Function):
     def backward(ctx, g_image, g_alpha, g_depth, *_unused):
         lib = _lib.load()
         meta = ctx.meta
-        rec, entry_ids, tile_ranges, bg, alpha, pix_state, n_consumed, tile_consumed = ctx.saved_tensors
+        rec, entry_ids, tile_ranges, bg, alpha, pix_state, tile_consumed = ctx.saved_tensors
         n = ctx.n
         dev = rec.device
         H, W = meta.H, meta.W
@@ -226,10 +229,10 @@ class _RasterizeFn(torch.autograd.Function):
             gi, ga, gd = dense(g_image, 3), dense(g_alpha, 1), dense(g_depth, 1)
             with _timed("raster_bwd", dev):
                 check(lib.gs_raster_bwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), ptr(alpha),
-                                        ptr(pix_state), ptr(n_consumed), ptr(tile_consumed), ptr(gi), ptr(ga), ptr(gd),
+                                        ptr(pix_state), ptr(tile_consumed), ptr(gi), ptr(ga), ptr(gd),
                                         ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                                         _stream(dev)), "gs_raster_bwd")
-        return None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None, None, None
+        return None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None, None, None, None
 
 
 def _is_parameter_model(g) -> bool:
@@ -348,7 +351,8 @@ class GaussianRenderer:
 
         # ---- stage R -----------------------------------------------------------------------
         image, alpha, depth, n_consumed, tile_consumed = _RasterizeFn.apply(
-            meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, num_vis > 0)
+            meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, num_vis > 0,
+            bool(getattr(settings, "debug", False)))
 
         self.last_stats = {"num_visible": num_vis, "num_binned": num_sorted, "tile_pairs": D}
         self._last_debug = {"tile_consumed": tile_consumed, "n_consumed": n_consumed, "entry_ids": entry_ids,

@@ -81,7 +81,7 @@ def cuda_render_with_grads(cam: so.OracleCamera, params, bg, weights=None, rende
     m = cuda_model_from_params(params)
     H, W = cam.height, cam.width
     rd = renderer or gb.GaussianRenderer()
-    out = rd.render(cuda_camera(cam), m, gb.RenderSettings(H, W, bg.cuda()))
+    out = rd.render(cuda_camera(cam), m, gb.RenderSettings(H, W, bg.cuda(), debug=True))   # debug: per-pixel n_consumed
     out["viewspace_points"].retain_grad()
     w = weights if weights is not None else so.loss_weights(H, W)
     loss = so.weighted_loss(out, tuple(t.cuda() for t in w))
@@ -99,3 +99,32 @@ def assert_same_ranges(got: torch.Tensor, want: torch.Tensor) -> None:
     assert torch.equal(got[:, 1] - got[:, 0], want[:, 1] - want[:, 0])
     nz = (want[:, 1] - want[:, 0]) > 0
     assert torch.equal(got[nz], want[nz])
+
+
+IMG_TOL = 1e-4          # BASELINE.json north_star: image / alpha / depth, absolute
+FLIP_TOL = 1e-2         # one contribution gained or lost at the A >= 0.995 test (<= 5e-3 on colour/alpha)
+FLIP_MAX_FRAC = 2e-3
+
+
+def assert_images_close(got, want, ncons_got, ncons_want, what=""):
+    """image/alpha/depth within IMG_TOL on every pixel whose walk ended at the same list entry as the
+    oracle's.  A pixel whose accumulated opacity crosses 0.995 one splat earlier or later (the one
+    discontinuity of the path; exp() differs in the last bits between CPU libm and the GPU's MUFU)
+    gains or loses a single contribution: those pixels are counted, bounded in number and deviation,
+    and reported -- the policy SURVEY 8c prescribes."""
+    ncg, ncw = ncons_got.cpu().long(), ncons_want.cpu().long()
+    same = (ncg == ncw)
+    flips = int((~same).sum())
+    assert flips <= max(2, int(FLIP_MAX_FRAC * same.numel())), f"{what}: {flips} termination flips of {same.numel()} pixels"
+    if flips:
+        assert int((ncg - ncw).abs().max()) <= 2, f"{what}: a pixel stops {int((ncg - ncw).abs().max())} entries away"
+    worst, worst_flip = {}, {}
+    for k in ("image", "alpha", "depth"):
+        d = (got[k].detach().cpu().double() - want[k].detach().cpu().double()).abs()
+        m = same.unsqueeze(0).expand_as(d)
+        worst[k] = float(d[m].max()) if bool(m.any()) else 0.0
+        worst_flip[k] = float(d[~m].max()) if flips else 0.0
+        assert worst[k] < IMG_TOL, f"{what}: {k} differs by {worst[k]:.3e}"
+        scale = 1.0 if k != "depth" else float(want[k].abs().max()) + 1.0
+        assert worst_flip[k] < FLIP_TOL * scale, f"{what}: {k} differs by {worst_flip[k]:.3e} on a flipped pixel"
+    return {"flips": flips, "worst": worst, "worst_flip": worst_flip}
