@@ -206,7 +206,8 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     // raster record: conic pre-scaled by c = -0.5*log2(e) so that exp(-0.5*s) = exp2(quadratic form)
     const float kC = -0.72134752044448170f;
     rec[i * 3 + 0] = make_float4(p.mx, p.my, kC * p.q00, kC * add_rn(p.q01, p.q10));
-    rec[i * 3 + 1] = make_float4(kC * p.q11, op, p.Z, cr);
+    // depth kept finite in the record: masked-out pixels multiply it by 0 (0*inf would be NaN)
+    rec[i * 3 + 1] = make_float4(kC * p.q11, op, fminf(p.Z, 3.0e38f), cr);
     rec[i * 3 + 2] = make_float4(cg, cb, 0.f, 0.f);
 }
 

@@ -27,11 +27,13 @@
 
 namespace gs {
 
-constexpr int kPx = 8;                 // pixels per lane (1x8 strip)
+constexpr int kPx = 8;                 // pixels per lane (1x8 strip) = 4 packed pairs
+constexpr int kPairs = kPx / 2;
 constexpr int kBatch = 32;             // list entries staged per round (one per lane)
 constexpr float kTermA = 0.995f;       // renderer.py:352
 constexpr float kMinW = 1e-5f;         // renderer.py:336
 constexpr float kLn2 = 0.69314718056f;
+constexpr float kNegHalfLog2e = -0.72134752044448170f;
 // Opacities at or below this are skipped as a whole (warp-uniform).  The reference skips a <= 0
 // (renderer.py:340); for 0 < opacity <= 1e-30 it would add < 1e-30 to every accumulator.
 constexpr float kTinyOpacity = 1e-30f;
@@ -47,25 +49,52 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// Per-entry values shared by a lane's 8 pixels.
+// Blackwell packed fp32: one issue slot, two IEEE-rounded fp32 results (FFMA2 / FADD2 / FMUL2).
+// Each lane keeps its 8 pixels as 4 (even, odd) pairs so the per-pixel arithmetic issues at half
+// the instruction count -- the kernels are issue-bound, so this is the sm_100-specific lever.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+
+// Per-entry values shared by a lane's 8 pixels, pre-broadcast into pairs.
 struct EntryRow {
-    float mx, q00, qsdy, q11dy2, op;
+    float2 neg_mx, q00, qsdy, q11dy2;
+    float op;
 };
 
-// renderer.py:330-346 for one pixel.  `A >= kTermA` encodes "this pixel has terminated (or lies
-// outside the image)", so no separate flag is carried.  Returns the predicate under which the
-// reference accumulates; w, a, contrib are always computed (branch-free).
-__device__ __forceinline__ bool eval_pixel(float px, const EntryRow& r, float A, float& dx, float& e, float& w,
-                                           float& a, float& contrib) {
-    dx = px - r.mx;
-    const float t = fmaf(r.q00, dx, r.qsdy);
-    const float sp = fmaf(dx, t, r.q11dy2);            // -0.5*log2(e) * s
-    e = ex2_approx(sp);
-    w = fminf(e, 1.0f);                                // clamp(exp(.), 0, 1); exp >= 0
-    a = __saturatef(mul_rn(r.op, w));                  // clamp(opacity * w, 0, 1)
-    contrib = mul_rn(sub_rn(1.0f, A), a);
+// renderer.py:330-346 for one pixel pair.  `A >= kTermA` encodes "this pixel has terminated (or
+// lies outside the image)", so no separate flag is carried.  Outputs: dx, e = exp(-s/2) (unclamped),
+// w = clamp(e), u = opacity*w (unclamped), contrib = (1-A)*clamp(u) ZEROED where the reference skips
+// the splat, and the two predicates.  Forward and backward both call this, so they agree bit for bit.
+struct PairEval {
+    float2 dx, e, w, u, a, T, contrib;
+    bool act0, act1;
+};
+
+__device__ __forceinline__ void eval_pair(float2 fpx, const EntryRow& r, float2 A, PairEval& ev) {
+    ev.dx = add2(fpx, r.neg_mx);
+    const float2 t = fma2(r.q00, ev.dx, r.qsdy);
+    const float2 sp = fma2(ev.dx, t, r.q11dy2);          // -0.5*log2(e) * s
+    ev.e = make_float2(ex2_approx(sp.x), ex2_approx(sp.y));
+    ev.w = make_float2(fminf(ev.e.x, 1.0f), fminf(ev.e.y, 1.0f));      // clamp(exp(.), 0, 1); exp >= 0
+    ev.u = mul2(bc2(r.op), ev.w);
+    ev.a = make_float2(__saturatef(ev.u.x), __saturatef(ev.u.y));      // clamp(opacity * w, 0, 1)
+    ev.T = fma2(A, bc2(-1.0f), bc2(1.0f));                              // 1 - A, one rounding
+    const float2 c = mul2(ev.T, ev.a);
     // a > 0 and contrib > 0 follow from opacity > kTinyOpacity, w >= 1e-5 and 1 - A >= 0.005
-    return (A < kTermA) && (w >= kMinW);
+    ev.act0 = (A.x < kTermA) && (ev.w.x >= kMinW);
+    ev.act1 = (A.y < kTermA) && (ev.w.y >= kMinW);
+    ev.contrib = make_float2(ev.act0 ? c.x : 0.f, ev.act1 ? c.y : 0.f);
+}
+
+__device__ __forceinline__ void load_entry_row(const float4& r0, const float4& r1, float fpy, EntryRow& row, float& dy) {
+    dy = fpy - r0.y;
+    row.neg_mx = bc2(-r0.x);
+    row.q00 = bc2(r0.z);
+    row.qsdy = bc2(r0.w * dy);
+    row.q11dy2 = bc2(r1.x * dy * dy);
+    row.op = r1.y;
 }
 
 template <bool kTrack>
@@ -84,17 +113,19 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     const int py = ty * kTile + (lane >> 1);
     const int px0 = tx * kTile + (lane & 1) * kPx;
     const float bg0 = bg_ptr[0], bg1 = bg_ptr[1], bg2 = bg_ptr[2];
-    const float fpy = (float)py, fpx0 = (float)px0;
+    const float fpy = (float)py;
 
-    float A[kPx], Cr[kPx], Cg[kPx], Cb[kPx], Ds[kPx];
+    float2 fpx[kPairs], A[kPairs], Cr[kPairs], Cg[kPairs], Cb[kPairs], Ds[kPairs];
     int ncons[kPx];
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        const bool inside = (px0 + k < img_w) && (py < img_h);
-        A[k] = inside ? 0.f : 2.0f;                     // 2.0: never alive
-        Ds[k] = 0.f;
-        Cr[k] = bg0; Cg[k] = bg1; Cb[k] = bg2;          // out_rgb starts at bg (renderer.py:273)
-        ncons[k] = -1;
+    for (int p = 0; p < kPairs; ++p) {
+        const bool in0 = (px0 + 2 * p < img_w) && (py < img_h);
+        const bool in1 = (px0 + 2 * p + 1 < img_w) && (py < img_h);
+        fpx[p] = make_float2((float)(px0 + 2 * p), (float)(px0 + 2 * p + 1));
+        A[p] = make_float2(in0 ? 0.f : 2.0f, in1 ? 0.f : 2.0f);          // 2.0: never alive
+        Ds[p] = bc2(0.f);
+        Cr[p] = bc2(bg0); Cg[p] = bc2(bg1); Cb[p] = bc2(bg2);            // out_rgb starts at bg (renderer.py:273)
+        ncons[2 * p] = ncons[2 * p + 1] = -1;
     }
 
     const int2 range = tile_ranges[tile];
@@ -102,7 +133,7 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     for (int base = range.x; base < range.y; base += kBatch) {
         bool alive = false;
 #pragma unroll
-        for (int k = 0; k < kPx; ++k) alive |= (A[k] < kTermA);
+        for (int p = 0; p < kPairs; ++p) alive |= (A[p].x < kTermA) | (A[p].y < kTermA);
         if (!__any_sync(0xffffffffu, alive)) break;
         const int cnt = min(kBatch, range.y - base);
         __syncwarp();                                   // previous batch fully read
@@ -119,19 +150,22 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
             const float4 r1 = srec[j * 3 + 1];          // q11', opacity, z, r
             const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);   // g, b
             if (!(r1.y > kTinyOpacity)) continue;       // warp-uniform
-            const float dy = fpy - r0.y;
             EntryRow row;
-            row.mx = r0.x; row.q00 = r0.z; row.qsdy = r0.w * dy; row.q11dy2 = r1.x * dy * dy; row.op = r1.y;
+            float dy;
+            load_entry_row(r0, r1, fpy, row, dy);
+            const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
 #pragma unroll
-            for (int k = 0; k < kPx; ++k) {
-                float dx, e, w, a, contrib;
-                if (eval_pixel(fpx0 + (float)k, row, A[k], dx, e, w, a, contrib)) {
-                    Cr[k] = fmaf(contrib, r1.w, Cr[k]);
-                    Cg[k] = fmaf(contrib, r2.x, Cg[k]);
-                    Cb[k] = fmaf(contrib, r2.y, Cb[k]);
-                    Ds[k] = fmaf(contrib, r1.z, Ds[k]);
-                    A[k] = add_rn(A[k], contrib);
-                    if (kTrack && A[k] >= kTermA) ncons[k] = base - range.x + j + 1;   // renderer.py:352
+            for (int p = 0; p < kPairs; ++p) {
+                PairEval ev;
+                eval_pair(fpx[p], row, A[p], ev);
+                Cr[p] = fma2(ev.contrib, cr, Cr[p]);
+                Cg[p] = fma2(ev.contrib, cg, Cg[p]);
+                Cb[p] = fma2(ev.contrib, cb, Cb[p]);
+                Ds[p] = fma2(ev.contrib, z, Ds[p]);
+                A[p] = add2(A[p], ev.contrib);
+                if (kTrack) {                           // renderer.py:352: the entry that terminates the pixel
+                    if (ev.act0 && A[p].x >= kTermA) ncons[2 * p] = base - range.x + j + 1;
+                    if (ev.act1 && A[p].y >= kTermA) ncons[2 * p + 1] = base - range.x + j + 1;
                 }
             }
         }
@@ -144,14 +178,19 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         const int px = px0 + k;
         if (px < img_w && py < img_h) {
             const int64_t p = (int64_t)py * img_w + px;
+            const float Ak = (k & 1) ? A[k >> 1].y : A[k >> 1].x;
+            const float Crk = (k & 1) ? Cr[k >> 1].y : Cr[k >> 1].x;
+            const float Cgk = (k & 1) ? Cg[k >> 1].y : Cg[k >> 1].x;
+            const float Cbk = (k & 1) ? Cb[k >> 1].y : Cb[k >> 1].x;
+            const float Dsk = (k & 1) ? Ds[k >> 1].y : Ds[k >> 1].x;
             float o_r, o_g, o_b, o_a, o_d;
             if (any_visible) {
-                const float om = sub_rn(1.f, A[k]);
-                o_r = __saturatef(add_rn(Cr[k], mul_rn(om, bg0)));
-                o_g = __saturatef(add_rn(Cg[k], mul_rn(om, bg1)));
-                o_b = __saturatef(add_rn(Cb[k], mul_rn(om, bg2)));
-                o_a = __saturatef(A[k]);
-                o_d = div_rn(Ds[k], add_rn(A[k], 1e-6f));
+                const float om = sub_rn(1.f, Ak);
+                o_r = __saturatef(add_rn(Crk, mul_rn(om, bg0)));
+                o_g = __saturatef(add_rn(Cgk, mul_rn(om, bg1)));
+                o_b = __saturatef(add_rn(Cbk, mul_rn(om, bg2)));
+                o_a = __saturatef(Ak);
+                o_d = div_rn(Dsk, add_rn(Ak, 1e-6f));
             } else {
                 o_r = bg0; o_g = bg1; o_b = bg2; o_a = 0.f; o_d = 0.f;
             }
@@ -160,7 +199,7 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
             image[2 * plane + p] = o_b;
             alpha[p] = o_a;
             depth[p] = o_d;
-            pix_state[p] = make_float4(Cr[k], Cg[k], Cb[k], Ds[k]);
+            pix_state[p] = make_float4(Crk, Cgk, Cbk, Dsk);
             if (kTrack) n_consumed[p] = ncons[k] >= 0 ? ncons[k] : walked;
         }
     }
@@ -175,9 +214,13 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 // so no reverse traversal and no division-recovered transmittance is needed.  Every non-final
 // contributor has a_k < 0.995 (else the pixel would have terminated there); for the terminating
 // contributor the suffix is exactly zero.
-// With s' = c*s (c = -0.5*log2 e) and w = 2^s':  dL/ds' = ln2 * w * dL/dw; the conic sums are
-// multiplied by c once per entry after the warp reduction.
+// With s' = c*s (c = -0.5*log2 e) and w = 2^s':  h = dL/ds' = ln2 * w * dL/dw.  Per lane only
+//   Sh = sum h,  Sx = sum h*dx,  Sxx = sum h*dx^2   (dy is the same for a lane's 8 pixels)
+// are accumulated; the five conic / mean sums follow once per entry:
+//   gQ00 = c*Sxx, gQ01 = gQ10 = c*dy*Sx, gQ11 = c*dy^2*Sh,
+//   g_mx = -(2 q00' Sx + qs' dy Sh),  g_my = -(2 q11' dy Sh + qs' Sx).
 constexpr int kRedVals = 10;     // mx my | q00 q01 q11 | opacity | z | r g b
+constexpr int kRedStride = 36;   // floats per value row: 32 lanes + pad, keeps LDS.128 aligned
 
 __global__ void __launch_bounds__(32)
 raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
@@ -190,7 +233,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                   float* __restrict__ g_colors, float* __restrict__ g_opac) {
     __shared__ float4 srec[kBatch * 3];
     __shared__ int sid[kBatch];
-    __shared__ float red[kRedVals][33];
+    __shared__ __align__(16) float red[kRedVals * kRedStride];
 
     const int tile = blockIdx.x;
     const int lane = threadIdx.x;
@@ -198,55 +241,63 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     const int py = ty * kTile + (lane >> 1);
     const int px0 = tx * kTile + (lane & 1) * kPx;
     const float bg0 = bg_ptr[0], bg1 = bg_ptr[1], bg2 = bg_ptr[2];
-    const float fpy = (float)py, fpx0 = (float)px0;
+    const float fpy = (float)py;
     const int64_t plane = (int64_t)img_w * img_h;
 
     // where lane v < 10 sends reduced value v:  target = out_base + id * out_stride
     float* out_base;
     int out_stride;
-    float out_scale = 1.0f;
-    const float kC = -0.72134752044448170f;            // -0.5 * log2(e)
     switch (lane) {
         case 0: out_base = g_means2d; out_stride = 2; break;
         case 1: out_base = g_means2d + 1; out_stride = 2; break;
-        case 2: out_base = g_conics; out_stride = 4; out_scale = kC; break;
-        case 3: out_base = g_conics + 1; out_stride = 4; out_scale = kC; break;   // Q01 (and Q10 below)
-        case 4: out_base = g_conics + 3; out_stride = 4; out_scale = kC; break;
+        case 2: out_base = g_conics; out_stride = 4; break;
+        case 3: out_base = g_conics + 1; out_stride = 4; break;   // Q01 (and Q10 below)
+        case 4: out_base = g_conics + 3; out_stride = 4; break;
         case 5: out_base = g_opac; out_stride = 1; break;
         case 6: out_base = g_depths; out_stride = 1; break;
         case 7: out_base = g_colors; out_stride = 3; break;
         case 8: out_base = g_colors + 1; out_stride = 3; break;
         default: out_base = g_colors + 2; out_stride = 3; break;
     }
-    const int red_v = lane % kRedVals, red_g = lane / kRedVals;      // lanes 0..29: value, third
+    // lanes 0..29: value red_v, third red_g of the 32 partials (12 + 12 + 8)
+    const int red_v = lane % kRedVals, red_g = lane / kRedVals;
+    const float4* red_src = reinterpret_cast<const float4*>(&red[red_v * kRedStride + red_g * 12]);
 
-    float A[kPx], P[kPx], Total[kPx], gCr[kPx], gCg[kPx], gCb[kPx], gDs[kPx], gA[kPx];
+    float2 fpx[kPairs], A[kPairs], P[kPairs], Total[kPairs], gCr[kPairs], gCg[kPairs], gCb[kPairs], gDs[kPairs], gA[kPairs];
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        const int px = px0 + k;
-        const bool inside = px < img_w && py < img_h;
-        A[k] = inside ? 0.f : 2.0f;
-        P[k] = 0.f;
-        Total[k] = gCr[k] = gCg[k] = gCb[k] = gDs[k] = gA[k] = 0.f;
-        if (inside) {
-            const int64_t p = (int64_t)py * img_w + px;
-            const float Af = alpha[p];                   // A is always inside [0,1], so alpha == A
-            const float4 st = pix_state[p];
-            const float om = sub_rn(1.f, Af);
-            const float pre_r = add_rn(st.x, mul_rn(om, bg0));
-            const float pre_g = add_rn(st.y, mul_rn(om, bg1));
-            const float pre_b = add_rn(st.z, mul_rn(om, bg2));
-            // torch.clamp passes the gradient on the closed interval
-            gCr[k] = (pre_r >= 0.f && pre_r <= 1.f) ? g_image[p] : 0.f;
-            gCg[k] = (pre_g >= 0.f && pre_g <= 1.f) ? g_image[plane + p] : 0.f;
-            gCb[k] = (pre_b >= 0.f && pre_b <= 1.f) ? g_image[2 * plane + p] : 0.f;
-            const float gd = g_depth[p];
-            const float den = add_rn(Af, 1e-6f);
-            gDs[k] = gd / den;
-            gA[k] = g_alpha[p] - (gCr[k] * bg0 + gCg[k] * bg1 + gCb[k] * bg2) - gd * st.w / (den * den);
-            Total[k] = gCr[k] * (st.x - bg0) + gCg[k] * (st.y - bg1) + gCb[k] * (st.z - bg2) + gDs[k] * st.w +
-                       gA[k] * Af;
+    for (int p = 0; p < kPairs; ++p) {
+        float Ai[2], Ti[2], gr[2], gg[2], gb[2], gd_[2], ga_[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int px = px0 + 2 * p + h;
+            const bool inside = px < img_w && py < img_h;
+            Ai[h] = inside ? 0.f : 2.0f;
+            Ti[h] = gr[h] = gg[h] = gb[h] = gd_[h] = ga_[h] = 0.f;
+            if (inside) {
+                const int64_t q = (int64_t)py * img_w + px;
+                const float Af = alpha[q];                   // A is always inside [0,1], so alpha == A
+                const float4 st = pix_state[q];
+                const float om = sub_rn(1.f, Af);
+                const float pre_r = add_rn(st.x, mul_rn(om, bg0));
+                const float pre_g = add_rn(st.y, mul_rn(om, bg1));
+                const float pre_b = add_rn(st.z, mul_rn(om, bg2));
+                // torch.clamp passes the gradient on the closed interval
+                gr[h] = (pre_r >= 0.f && pre_r <= 1.f) ? g_image[q] : 0.f;
+                gg[h] = (pre_g >= 0.f && pre_g <= 1.f) ? g_image[plane + q] : 0.f;
+                gb[h] = (pre_b >= 0.f && pre_b <= 1.f) ? g_image[2 * plane + q] : 0.f;
+                const float gd = g_depth[q];
+                const float den = add_rn(Af, 1e-6f);
+                gd_[h] = gd / den;
+                ga_[h] = g_alpha[q] - (gr[h] * bg0 + gg[h] * bg1 + gb[h] * bg2) - gd * st.w / (den * den);
+                Ti[h] = gr[h] * (st.x - bg0) + gg[h] * (st.y - bg1) + gb[h] * (st.z - bg2) + gd_[h] * st.w + ga_[h] * Af;
+            }
         }
+        fpx[p] = make_float2((float)(px0 + 2 * p), (float)(px0 + 2 * p + 1));
+        A[p] = make_float2(Ai[0], Ai[1]);
+        P[p] = bc2(0.f);
+        Total[p] = make_float2(Ti[0], Ti[1]);
+        gCr[p] = make_float2(gr[0], gr[1]); gCg[p] = make_float2(gg[0], gg[1]); gCb[p] = make_float2(gb[0], gb[1]);
+        gDs[p] = make_float2(gd_[0], gd_[1]); gA[p] = make_float2(ga_[0], ga_[1]);
     }
 
     const int2 range = tile_ranges[tile];
@@ -254,7 +305,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     for (int base = range.x; base < end; base += kBatch) {
         bool alive = false;
 #pragma unroll
-        for (int k = 0; k < kPx; ++k) alive |= (A[k] < kTermA);
+        for (int p = 0; p < kPairs; ++p) alive |= (A[p].x < kTermA) | (A[p].y < kTermA);
         if (!__any_sync(0xffffffffu, alive)) break;
         const int cnt = min(kBatch, end - base);
         __syncwarp();
@@ -270,63 +321,77 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
             const float4 r0 = srec[j * 3 + 0];
             const float4 r1 = srec[j * 3 + 1];
             const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);
-            const float op = r1.y, z = r1.z;
+            const float op = r1.y;
             if (!(op > kTinyOpacity)) continue;         // warp-uniform
-            const float dy = fpy - r0.y;
             EntryRow row;
-            row.mx = r0.x; row.q00 = r0.z; row.qsdy = r0.w * dy; row.q11dy2 = r1.x * dy * dy; row.op = op;
-            const float two_q00 = 2.f * r0.z, two_q11dy = 2.f * r1.x * dy, dy2 = dy * dy;
-            float a_mx = 0.f, a_my = 0.f, a_q00 = 0.f, a_q01 = 0.f, a_q11 = 0.f, a_op = 0.f, a_z = 0.f;
-            float a_cr = 0.f, a_cg = 0.f, a_cb = 0.f;
-            bool any = false;
+            float dy;
+            load_entry_row(r0, r1, fpy, row, dy);
+            const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
+            const float2 hscale = bc2(kLn2 * op);
+            float2 s_h = bc2(0.f), s_x = bc2(0.f), s_xx = bc2(0.f), s_op = bc2(0.f), s_z = bc2(0.f);
+            float2 s_cr = bc2(0.f), s_cg = bc2(0.f), s_cb = bc2(0.f), s_c = bc2(0.f);
 #pragma unroll
-            for (int k = 0; k < kPx; ++k) {
-                float dx, e, w, a, contrib;
-                const float T = sub_rn(1.f, A[k]);
-                if (eval_pixel(fpx0 + (float)k, row, A[k], dx, e, w, a, contrib)) {
-                    any = true;
-                    const float v = fmaf(gCr[k], r1.w, fmaf(gCg[k], r2.x, fmaf(gCb[k], r2.y, fmaf(gDs[k], z, gA[k]))));
-                    P[k] = fmaf(contrib, v, P[k]);
-                    A[k] = add_rn(A[k], contrib);
-                    // terminating contributor: empty suffix.  Otherwise a < 0.995, so 1 - a >= 0.005.
-                    const float suffix = (A[k] >= kTermA) ? 0.f : (Total[k] - P[k]) * rcp_approx(1.f - a);
-                    const float g_a = fmaf(T, v, -suffix);
-                    a_cr = fmaf(contrib, gCr[k], a_cr);
-                    a_cg = fmaf(contrib, gCg[k], a_cg);
-                    a_cb = fmaf(contrib, gCb[k], a_cb);
-                    a_z = fmaf(contrib, gDs[k], a_z);
-                    // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
-                    const bool pass_a = mul_rn(op, w) <= 1.f;
-                    const float g_aw = pass_a ? g_a : 0.f;
-                    a_op = fmaf(g_aw, w, a_op);
-                    const float h = (e <= 1.f) ? (kLn2 * w) * (g_aw * op) : 0.f;     // dL/ds'
-                    a_q00 = fmaf(dx * dx, h, a_q00);
-                    a_q01 = fmaf(dx * dy, h, a_q01);
-                    a_q11 = fmaf(dy2, h, a_q11);
-                    a_mx = fmaf(-h, fmaf(two_q00, dx, r0.w * dy), a_mx);
-                    a_my = fmaf(-h, fmaf(r0.w, dx, two_q11dy), a_my);
-                }
+            for (int p = 0; p < kPairs; ++p) {
+                PairEval ev;
+                eval_pair(fpx[p], row, A[p], ev);
+                const float2 v = fma2(gCr[p], cr, fma2(gCg[p], cg, fma2(gCb[p], cb, fma2(gDs[p], z, gA[p]))));
+                P[p] = fma2(ev.contrib, v, P[p]);
+                A[p] = add2(A[p], ev.contrib);
+                s_c = add2(s_c, ev.contrib);
+                // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
+                // a < 0.995, so 1 - a >= 0.005 and the approximate reciprocal is safe.
+                const float2 oma = fma2(ev.a, bc2(-1.0f), bc2(1.0f));
+                const float2 nrem = fma2(Total[p], bc2(-1.0f), P[p]);          // -(Total - prefix)
+                float2 nsuf = mul2(nrem, make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
+                nsuf.x = (A[p].x >= kTermA) ? 0.f : nsuf.x;
+                nsuf.y = (A[p].y >= kTermA) ? 0.f : nsuf.y;
+                float2 g_a = fma2(ev.T, v, nsuf);
+                // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
+                g_a.x = (ev.act0 && ev.u.x <= 1.f) ? g_a.x : 0.f;
+                g_a.y = (ev.act1 && ev.u.y <= 1.f) ? g_a.y : 0.f;
+                s_op = fma2(g_a, ev.w, s_op);
+                float2 h = mul2(mul2(ev.w, g_a), hscale);                      // dL/ds'
+                h.x = (ev.e.x <= 1.f) ? h.x : 0.f;
+                h.y = (ev.e.y <= 1.f) ? h.y : 0.f;
+                const float2 hdx = mul2(h, ev.dx);
+                s_h = add2(s_h, h);
+                s_x = add2(s_x, hdx);
+                s_xx = fma2(hdx, ev.dx, s_xx);
+                s_cr = fma2(ev.contrib, gCr[p], s_cr);
+                s_cg = fma2(ev.contrib, gCg[p], s_cg);
+                s_cb = fma2(ev.contrib, gCb[p], s_cb);
+                s_z = fma2(ev.contrib, gDs[p], s_z);
             }
-            if (!__any_sync(0xffffffffu, any)) continue;
-            // transpose-reduce the 10 sums over the warp: red[v][lane], row stride 33 (conflict-free)
-            red[0][lane] = a_mx;  red[1][lane] = a_my;
-            red[2][lane] = a_q00; red[3][lane] = a_q01; red[4][lane] = a_q11;
-            red[5][lane] = a_op;  red[6][lane] = a_z;
-            red[7][lane] = a_cr;  red[8][lane] = a_cg;  red[9][lane] = a_cb;
+            if (!__any_sync(0xffffffffu, (s_c.x + s_c.y) > 0.f)) continue;
+            const float Sh = s_h.x + s_h.y, Sx = s_x.x + s_x.y, Sxx = s_xx.x + s_xx.y;
+            const float dySh = dy * Sh;
+            // transpose-reduce the 10 sums over the warp: red[v][lane]
+            red[0 * kRedStride + lane] = -fmaf(2.f * r0.z, Sx, r0.w * dySh);             // g_mx
+            red[1 * kRedStride + lane] = -fmaf(2.f * r1.x, dySh, r0.w * Sx);             // g_my
+            red[2 * kRedStride + lane] = kNegHalfLog2e * Sxx;                            // g_Q00
+            red[3 * kRedStride + lane] = kNegHalfLog2e * (dy * Sx);                      // g_Q01 = g_Q10
+            red[4 * kRedStride + lane] = kNegHalfLog2e * (dy * dySh);                    // g_Q11
+            red[5 * kRedStride + lane] = s_op.x + s_op.y;
+            red[6 * kRedStride + lane] = s_z.x + s_z.y;
+            red[7 * kRedStride + lane] = s_cr.x + s_cr.y;
+            red[8 * kRedStride + lane] = s_cg.x + s_cg.y;
+            red[9 * kRedStride + lane] = s_cb.x + s_cb.y;
             __syncwarp();
             float s = 0.f;
             if (lane < 30) {
-                const float* rowp = &red[red_v][red_g * 11];
-#pragma unroll
-                for (int t = 0; t < 10; ++t) s += rowp[t];
-                if (red_g < 2) s += rowp[10];            // thirds cover 11 + 11 + 10 lanes
+                const float4 q0 = red_src[0], q1 = red_src[1];
+                s = (q0.x + q0.y) + (q0.z + q0.w) + (q1.x + q1.y) + (q1.z + q1.w);
+                if (red_g < 2) {
+                    const float4 q2 = red_src[2];
+                    s += (q2.x + q2.y) + (q2.z + q2.w);
+                }
             }
             __syncwarp();
             // lane v < 10 collects the three thirds of value v (lanes v, v+10, v+20)
             const float s2 = __shfl_down_sync(0xffffffffu, s, 10);
             const float s3 = __shfl_down_sync(0xffffffffu, s, 20);
             if (lane < kRedVals) {
-                const float total = (s + s2 + s3) * out_scale;
+                const float total = s + s2 + s3;
                 float* dst = out_base + (int64_t)sid[j] * out_stride;
                 atomicAdd(dst, total);
                 if (lane == 3) atomicAdd(dst + 1, total);      // Q01 and Q10 enter s symmetrically
