@@ -82,7 +82,10 @@ __device__ __forceinline__ void eval_pair(float2 fpx, const EntryRow& r, float2 
     ev.a = make_float2(__saturatef(ev.u.x), __saturatef(ev.u.y));      // clamp(opacity * w, 0, 1)
     ev.T = fma2(A, bc2(-1.0f), bc2(1.0f));                              // 1 - A, one rounding
     const float2 c = mul2(ev.T, ev.a);
-    // a > 0 and contrib > 0 follow from opacity > kTinyOpacity, w >= 1e-5 and 1 - A >= 0.005
+    // a > 0 and contrib > 0 follow from opacity > kTinyOpacity, w >= 1e-5 and 1 - A >= 0.005;
+    // entries with opacity <= kTinyOpacity were staged with opacity 0 and contribute exact zeros
+    // (a = 0 => contrib = 0; the backward skips such an entry as a whole because its sum of
+    // contributions is zero)
     ev.act0 = (A.x < kTermA) && (ev.w.x >= kMinW);
     ev.act1 = (A.y < kTermA) && (ev.w.y >= kMinW);
     ev.contrib = make_float2(ev.act0 ? c.x : 0.f, ev.act1 ? c.y : 0.f);
@@ -139,17 +142,19 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         __syncwarp();                                   // previous batch fully read
         if (lane < cnt) {
             const int id = entry_ids[base + lane];
+            float4 q1 = __ldg(&rec[(int64_t)id * 3 + 1]);
+            q1.y = (q1.y > kTinyOpacity) ? q1.y : 0.f;      // opacity 0 => a = 0 => the entry adds exact zeros
             srec[lane * 3 + 0] = __ldg(&rec[(int64_t)id * 3 + 0]);
-            srec[lane * 3 + 1] = __ldg(&rec[(int64_t)id * 3 + 1]);
+            srec[lane * 3 + 1] = q1;
             srec[lane * 3 + 2] = __ldg(&rec[(int64_t)id * 3 + 2]);
         }
         __syncwarp();
         walked = base - range.x + cnt;
+#pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
             const float4 r0 = srec[j * 3 + 0];          // mx, my, q00', qs'
-            const float4 r1 = srec[j * 3 + 1];          // q11', opacity, z, r
+            const float4 r1 = srec[j * 3 + 1];          // q11', opacity (0 if tiny), z, r
             const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);   // g, b
-            if (!(r1.y > kTinyOpacity)) continue;       // warp-uniform
             EntryRow row;
             float dy;
             load_entry_row(r0, r1, fpy, row, dy);
@@ -222,7 +227,7 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 constexpr int kRedVals = 10;     // mx my | q00 q01 q11 | opacity | z | r g b
 constexpr int kRedStride = 36;   // floats per value row: 32 lanes + pad, keeps LDS.128 aligned
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 16)
 raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, const float* __restrict__ alpha,
@@ -263,7 +268,8 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     const int red_v = lane % kRedVals, red_g = lane / kRedVals;
     const float4* red_src = reinterpret_cast<const float4*>(&red[red_v * kRedStride + red_g * 12]);
 
-    float2 fpx[kPairs], A[kPairs], P[kPairs], Total[kPairs], gCr[kPairs], gCg[kPairs], gCb[kPairs], gDs[kPairs], gA[kPairs];
+    // R = -(Total - prefix): minus what the contributors still to come will add (the suffix sum)
+    float2 fpx[kPairs], A[kPairs], R[kPairs], gCr[kPairs], gCg[kPairs], gCb[kPairs], gDs[kPairs], gA[kPairs];
 #pragma unroll
     for (int p = 0; p < kPairs; ++p) {
         float Ai[2], Ti[2], gr[2], gg[2], gb[2], gd_[2], ga_[2];
@@ -294,8 +300,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         }
         fpx[p] = make_float2((float)(px0 + 2 * p), (float)(px0 + 2 * p + 1));
         A[p] = make_float2(Ai[0], Ai[1]);
-        P[p] = bc2(0.f);
-        Total[p] = make_float2(Ti[0], Ti[1]);
+        R[p] = make_float2(-Ti[0], -Ti[1]);
         gCr[p] = make_float2(gr[0], gr[1]); gCg[p] = make_float2(gg[0], gg[1]); gCb[p] = make_float2(gb[0], gb[1]);
         gDs[p] = make_float2(gd_[0], gd_[1]); gA[p] = make_float2(ga_[0], ga_[1]);
     }
@@ -312,8 +317,10 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         if (lane < cnt) {
             const int id = entry_ids[base + lane];
             sid[lane] = id;
+            float4 q1 = __ldg(&rec[(int64_t)id * 3 + 1]);
+            q1.y = (q1.y > kTinyOpacity) ? q1.y : 0.f;
             srec[lane * 3 + 0] = __ldg(&rec[(int64_t)id * 3 + 0]);
-            srec[lane * 3 + 1] = __ldg(&rec[(int64_t)id * 3 + 1]);
+            srec[lane * 3 + 1] = q1;
             srec[lane * 3 + 2] = __ldg(&rec[(int64_t)id * 3 + 2]);
         }
         __syncwarp();
@@ -322,27 +329,24 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
             const float4 r1 = srec[j * 3 + 1];
             const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);
             const float op = r1.y;
-            if (!(op > kTinyOpacity)) continue;         // warp-uniform
             EntryRow row;
             float dy;
             load_entry_row(r0, r1, fpy, row, dy);
             const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
             const float2 hscale = bc2(kLn2 * op);
             float2 s_h = bc2(0.f), s_x = bc2(0.f), s_xx = bc2(0.f), s_op = bc2(0.f), s_z = bc2(0.f);
-            float2 s_cr = bc2(0.f), s_cg = bc2(0.f), s_cb = bc2(0.f), s_c = bc2(0.f);
+            float2 s_cr = bc2(0.f), s_cg = bc2(0.f), s_cb = bc2(0.f);
 #pragma unroll
             for (int p = 0; p < kPairs; ++p) {
                 PairEval ev;
                 eval_pair(fpx[p], row, A[p], ev);
                 const float2 v = fma2(gCr[p], cr, fma2(gCg[p], cg, fma2(gCb[p], cb, fma2(gDs[p], z, gA[p]))));
-                P[p] = fma2(ev.contrib, v, P[p]);
+                R[p] = fma2(ev.contrib, v, R[p]);
                 A[p] = add2(A[p], ev.contrib);
-                s_c = add2(s_c, ev.contrib);
                 // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
                 // a < 0.995, so 1 - a >= 0.005 and the approximate reciprocal is safe.
                 const float2 oma = fma2(ev.a, bc2(-1.0f), bc2(1.0f));
-                const float2 nrem = fma2(Total[p], bc2(-1.0f), P[p]);          // -(Total - prefix)
-                float2 nsuf = mul2(nrem, make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
+                float2 nsuf = mul2(R[p], make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
                 nsuf.x = (A[p].x >= kTermA) ? 0.f : nsuf.x;
                 nsuf.y = (A[p].y >= kTermA) ? 0.f : nsuf.y;
                 float2 g_a = fma2(ev.T, v, nsuf);
@@ -362,7 +366,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                 s_cb = fma2(ev.contrib, gCb[p], s_cb);
                 s_z = fma2(ev.contrib, gDs[p], s_z);
             }
-            if (!__any_sync(0xffffffffu, (s_c.x + s_c.y) > 0.f)) continue;
+            if (!(op > 0.f)) continue;      // staged as 0 when <= kTinyOpacity: the reference skips a <= 0 (warp-uniform)
             const float Sh = s_h.x + s_h.y, Sx = s_x.x + s_x.y, Sxx = s_xx.x + s_xx.y;
             const float dySh = dy * Sh;
             // transpose-reduce the 10 sums over the warp: red[v][lane]
