@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 4
+#define GS_ABI_VERSION 5
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -130,13 +130,20 @@ int gs_project_bwd(int64_t n,
  *                   counters[0] = splats with >= 1 tile, counters[1] = D (tile pairs),
  *                   counters[2] = splats that passed culling (3 x int64)
  *   -- caller reads the counters back (the one host sync of the frame) --
- *   gs_bin_sort:    duplication in depth order, stable radix sort on the tile id alone,
- *                   tile-range extraction.
+ *   gs_bin_sort:    groups the pairs by tile, keeping depth order.  algo GS_BIN_COUNTING (default via
+ *                   GS_BIN_AUTO): hand-written stable chunked counting sort (per-chunk shared-memory
+ *                   tile counters walked in depth order, column scan, parallel scatter);
+ *                   GS_BIN_RADIX: duplication + library (CUB) radix sort on the tile id + range
+ *                   extraction -- kept for tile grids too large for the counters and as a cross-check.
  * Outputs: entry_ids [D] int32 splat ids grouped by tile, front to back;
  *          tile_ranges [num_tiles,2] int32 = [begin,end) into entry_ids;
  *          entry_keys [D] uint64 (optional, may be NULL) = tile_id<<32 | depth_bits of each entry,
  *          for parity checks against the reference order.
  * ------------------------------------------------------------------------------------- */
+#define GS_BIN_AUTO 0
+#define GS_BIN_COUNTING 1
+#define GS_BIN_RADIX 2
+
 int64_t gs_bin_workspace_bytes(int64_t n, int64_t d_capacity, int32_t num_tiles);
 
 int gs_bin_prepare(int64_t n,
@@ -148,7 +155,7 @@ int gs_bin_prepare(int64_t n,
 int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
                 const int32_t* sorted_ids, const int64_t* offsets,
                 const uint16_t* tile_rect, const uint32_t* depth_keys,
-                int32_t tiles_x, int32_t num_tiles,
+                int32_t tiles_x, int32_t num_tiles, int32_t algo,
                 void* workspace, int64_t workspace_bytes,
                 int32_t* entry_ids, int32_t* tile_ranges, uint64_t* entry_keys,
                 void* stream);

@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LIB_NAME = "libgsplat_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
@@ -28,7 +28,7 @@ SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "gs_bin_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
     "gs_bin_prepare": (c_int32, [c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
-    "gs_bin_sort": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, c_int32,
+    "gs_bin_sort": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,
                                _P, c_int64, _P, _P, _P, _P]),
     "gs_raster_fwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32,
                                  _P, _P, _P, _P, _P, _P, _P]),

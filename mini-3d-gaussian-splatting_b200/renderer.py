@@ -262,6 +262,7 @@ class GaussianRenderer:
         self.radius_max = radius_max
         self.device = torch.device("cuda")
         self.last_stats: Dict[str, int] = {}
+        self.bin_algo = 0          # GS_BIN_AUTO; 1 = counting sort, 2 = library radix sort (cross-check)
         _lib.load()   # fail at construction, not at first render, if the extension is missing
 
     # ------------------------------------------------------------------------------------
@@ -340,13 +341,13 @@ class GaussianRenderer:
         num_sorted, D, num_vis = (int(v) for v in counters.tolist())
         tile_ranges = torch.empty((num_tiles, 2), dtype=_I32, device=device)
         entry_ids = torch.empty(max(D, 1), dtype=_I32, device=device)
-        ws_bytes = int(lib.gs_bin_workspace_bytes(0, D, num_tiles))
+        ws_bytes = int(lib.gs_bin_workspace_bytes(num_sorted, D, num_tiles))
         if ws.numel() < ws_bytes:
             ws = torch.empty(ws_bytes, dtype=_U8, device=device)
         with _timed("bin_sort", device):
             check(lib.gs_bin_sort(n, num_sorted, D, ptr(sorted_ids), ptr(offsets), ptr(tile_rect), ptr(depth_keys),
-                                  tiles_x, num_tiles, ptr(ws), ws.numel(), ptr(entry_ids), ptr(tile_ranges), None,
-                                  stream), "gs_bin_sort")
+                                  tiles_x, num_tiles, int(self.bin_algo), ptr(ws), ws.numel(), ptr(entry_ids),
+                                  ptr(tile_ranges), None, stream), "gs_bin_sort")
         entry_ids = entry_ids[:D]
 
         # ---- stage R -----------------------------------------------------------------------

@@ -270,10 +270,13 @@ def test_sort_keys_bit_exact_vs_oracle():
     entry_ids = torch.empty(D, dtype=torch.int32, device="cuda")
     ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device="cuda")
     ekeys = torch.empty(D, dtype=torch.int64, device="cuda")
-    _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
-                               P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), st), "sort")
-    assert torch.equal(ekeys.cpu(), o["sort_keys"])
-    assert torch.equal(entry_ids.cpu().long(), o["sort_ids"])
+    for algo in (1, 2):          # hand-written counting sort, library radix sort: identical sequences
+        entry_ids.fill_(-1); ekeys.fill_(-1)
+        _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
+                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), st), "sort")
+        assert torch.equal(ekeys.cpu(), o["sort_keys"]), algo
+        assert torch.equal(entry_ids.cpu().long(), o["sort_ids"]), algo
+        util.assert_same_ranges(ranges, o["tile_ranges"])
 
 
 def test_all_invisible_returns_background_once_unclamped_and_zero_grads():
