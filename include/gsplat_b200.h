@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 5
+#define GS_ABI_VERSION 6
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -44,12 +44,13 @@ typedef enum GsStatus {
     GS_ERR_UNSUPPORTED = -4
 } GsStatus;
 
-/* Camera block, HOST memory, 16 floats:
+/* Camera block, HOST memory, 20 floats:
  *   [0..8]  Rv  row-major 3x3  = world_view_transform()[:3,:3]      renderer.py:150-151
  *   [9..11] Tv                 = world_view_transform()[:3,3]       renderer.py:152
  *   [12] fx = 0.5*W/tan(FoVx/2)  [13] fy = 0.5*H/tan(FoVy/2)  [14] cx = W/2  [15] cy = H/2   renderer.py:142-147
+ *   [16..18] camera centre in world space, -Rv^T Tv (only read when sh_degree > 0)   [19] unused
  * (computed in double on the host and rounded once to fp32, as the reference does). */
-#define GS_CAMERA_FLOATS 16
+#define GS_CAMERA_FLOATS 20
 
 /* Per-splat record consumed by the raster kernels: 12 floats = 3 x float4, 48-byte stride.
  *   {mx, my, c*Q00, c*(Q01+Q10)} {c*Q11, opacity, depth, r} {g, b, 0, 0},  c = -0.5*log2(e):
@@ -75,6 +76,11 @@ int64_t gs_kernel_launch_count(void);
  * opacity: [n]; a logit when opacity_is_logit != 0 (sigmoid is fused), else already activated.
  * feat0:   pointer to features[0,0,0]; row i, channel c is feat0[i*feat_stride + c]; the colour
  *          is sigmoid(features[:,0,:]) (renderer.py:88-92).
+ * sh_rest / sh_rest_stride / sh_degree: optional view-dependent colour (an extension: the reference
+ *          is DC-only).  sh_degree 0 (default) ignores sh_rest.  For degree d in 1..3 the colour is
+ *          sigmoid(features[:,0,:] + sum_{k=1}^{(d+1)^2-1} Y_k(dir) features[:,k,:]) with the real SH
+ *          basis and dir = normalize(xyz - camera centre); row k >= 1, channel c of splat i is
+ *          sh_rest[i*sh_rest_stride + (k-1)*3 + c].  Identical to degree 0 when those rows are zero.
  *
  * Outputs (all length n, invisible splats included -- renderer.py:106-114):
  *   means2d [n,2]  depths [n]  conics [n,2,2]  radii [n] (float)  colors [n,3]  opacities [n]
@@ -91,6 +97,7 @@ int gs_project_fwd(int64_t n,
                    const float* cov3d,
                    const float* opacity, int32_t opacity_is_logit,
                    const float* feat0, int64_t feat_stride,
+                   const float* sh_rest, int64_t sh_rest_stride, int32_t sh_degree,
                    const float* camera_host,
                    int32_t img_w, int32_t img_h, int32_t tile_size,
                    float radius_min, float radius_max,
@@ -104,19 +111,22 @@ int gs_project_fwd(int64_t n,
  * g_depths [n], g_colors [n,3], g_opacities [n].  Results are WRITTEN (not accumulated):
  *   g_xyz [n,3]; parameter mode: g_scaling_log [n,3], g_rotation [n,4]; covariance mode: g_cov3d [n,3,3];
  *   g_opacity [n] (w.r.t. the logit when opacity_is_logit, else w.r.t. the activated value);
- *   g_feat0: row i channel c at g_feat0[i*g_feat_stride + c]; other feature rows are the
- *            caller's to zero (the reference yields zeros there -- SURVEY 3.2). */
+ *   g_feat0: row i channel c at g_feat0[i*g_feat_stride + c]; with sh_degree 0 the other feature
+ *            rows are the caller's to zero (the reference yields zeros there -- SURVEY 3.2);
+ *   g_sh_rest (sh_degree > 0): all 15 higher-order rows are written (rows beyond the degree as 0). */
 int gs_project_bwd(int64_t n,
                    const float* xyz,
                    const float* scaling_log, const float* rotation,
                    const float* cov3d,
                    const float* opacity, int32_t opacity_is_logit,
                    const float* feat0, int64_t feat_stride,
+                   const float* sh_rest, int64_t sh_rest_stride, int32_t sh_degree,
                    const float* camera_host,
                    const float* g_means2d, const float* g_conics, const float* g_depths,
                    const float* g_colors, const float* g_opacities,
                    float* g_xyz, float* g_scaling_log, float* g_rotation, float* g_cov3d,
                    float* g_opacity, float* g_feat0, int64_t g_feat_stride,
+                   float* g_sh_rest, int64_t g_sh_rest_stride,
                    void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -8,4 +8,5 @@ from .renderer import GaussianRenderer, RenderSettings  # noqa: F401
 from .scene import Camera, GaussianModel  # noqa: F401
 
 __all__ = ["GaussianRenderer", "RenderSettings", "GaussianModel", "Camera"]
-from . import multiview  # noqa: F401,E402
+from . import multiview, training  # noqa: F401,E402
+from .training import DensityController, GaussianOptimizer, LearningRateScheduler, TrainingConfig, train_step  # noqa: F401,E402

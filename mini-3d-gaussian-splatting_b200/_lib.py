@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LIB_NAME = "libgsplat_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
@@ -20,12 +20,12 @@ SIGNATURES = {
     "gs_last_error_string": (c_char_p, []),
     "gs_built_for_sm": (c_int32, []),
     "gs_kernel_launch_count": (c_int64, []),
-    "gs_project_fwd": (c_int32, [c_int64, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P,
+    "gs_project_fwd": (c_int32, [c_int64, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P, c_int64, c_int32, _P,
                                   c_int32, c_int32, c_int32, c_float, c_float,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "gs_project_bwd": (c_int32, [c_int64, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P,
+    "gs_project_bwd": (c_int32, [c_int64, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P, c_int64, c_int32, _P,
                                   _P, _P, _P, _P, _P,
-                                  _P, _P, _P, _P, _P, _P, c_int64, _P]),
+                                  _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P]),
     "gs_bin_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
     "gs_bin_prepare": (c_int32, [c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
     "gs_bin_sort": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,

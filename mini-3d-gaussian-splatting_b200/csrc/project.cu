@@ -137,19 +137,108 @@ __device__ __forceinline__ void project_point(const Camera& cam, float x0, float
 
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-template <bool kParamMode>
+// ---- optional view-dependent colour: real spherical harmonics up to degree 3 -----------------------
+// The reference renders sigmoid(features[:,0,:]) only (renderer.py:88-92; its SH evaluator is a stub,
+// math_utils.py:44-49).  With sh_degree > 0 the colour becomes
+//     sigmoid( features[:,0,:] + sum_{k=1}^{(deg+1)^2-1} Y_k(dir) * features[:,k,:] ),   dir = normalize(xyz - camera centre),
+// with the usual real-SH basis; it equals the reference bit for bit whenever the higher-order rows are
+// zero (the reference's initialisation, gaussian_model.py:84).  Default is sh_degree = 0.
+struct ShParams {
+    const float* rest;        // features row 1 of splat 0; row k (>=1), channel c of splat i at rest[i*stride + (k-1)*3 + c]
+    long long stride;
+    float* g_rest;            // backward only
+    long long g_stride;
+    int degree;               // 0..3
+    int staged;               // rest is [n,15,3] contiguous: stage through shared memory with float4 loads
+    float cx, cy, cz;         // camera centre in world space
+};
+constexpr int kShRest = 15;
+constexpr int kShRowFloats = kShRest * 3;
+
+__device__ __forceinline__ int sh_terms(int degree) { return (degree + 1) * (degree + 1) - 1; }
+
+// Y[0..14] = basis for k = 1..15 at unit direction (x,y,z)
+__device__ __forceinline__ void sh_basis(int degree, float x, float y, float z, float* Y) {
+    const float C1 = 0.4886025119029199f;
+    Y[0] = -C1 * y; Y[1] = C1 * z; Y[2] = -C1 * x;
+    if (degree < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    Y[3] = 1.0925484305920792f * xy;
+    Y[4] = -1.0925484305920792f * yz;
+    Y[5] = 0.31539156525252005f * (2.f * zz - xx - yy);
+    Y[6] = -1.0925484305920792f * xz;
+    Y[7] = 0.5462742152960396f * (xx - yy);
+    if (degree < 3) return;
+    Y[8] = -0.5900435899266435f * y * (3.f * xx - yy);
+    Y[9] = 2.890611442640554f * xy * z;
+    Y[10] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+    Y[11] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    Y[12] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+    Y[13] = 1.445305721320277f * z * (xx - yy);
+    Y[14] = -0.5900435899266435f * x * (xx - 3.f * yy);
+}
+
+// g_dir = sum_k s[k] * grad Y_k
+__device__ __forceinline__ void sh_basis_grad(int degree, float x, float y, float z, const float* s, float& gx, float& gy, float& gz) {
+    const float C1 = 0.4886025119029199f;
+    gx = -C1 * s[2]; gy = -C1 * s[0]; gz = C1 * s[1];
+    if (degree < 2) return;
+    const float a = 1.0925484305920792f, b = 0.31539156525252005f, c = 0.5462742152960396f;
+    gx += a * y * s[3] - 2.f * b * x * s[5] - a * z * s[6] + 2.f * c * x * s[7];
+    gy += a * x * s[3] - a * z * s[4] - 2.f * b * y * s[5] - 2.f * c * y * s[7];
+    gz += -a * y * s[4] + 4.f * b * z * s[5] - a * x * s[6];
+    if (degree < 3) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    const float d0 = -0.5900435899266435f, d1 = 2.890611442640554f, d2 = -0.4570457994644658f,
+                d3 = 0.3731763325901154f, d5 = 1.445305721320277f;
+    gx += d0 * 6.f * xy * s[8] + d1 * yz * s[9] + d2 * (-2.f * xy) * s[10] + d3 * (-6.f * xz) * s[11] +
+          d2 * (4.f * zz - 3.f * xx - yy) * s[12] + d5 * 2.f * xz * s[13] + d0 * (3.f * xx - 3.f * yy) * s[14];
+    gy += d0 * (3.f * xx - 3.f * yy) * s[8] + d1 * xz * s[9] + d2 * (4.f * zz - xx - 3.f * yy) * s[10] + d3 * (-6.f * yz) * s[11] +
+          d2 * (-2.f * xy) * s[12] + d5 * (-2.f * yz) * s[13] + d0 * (-6.f * xy) * s[14];
+    gz += d1 * xy * s[9] + d2 * 8.f * yz * s[10] + d3 * (6.f * zz - 3.f * xx - 3.f * yy) * s[11] + d2 * 8.f * xz * s[12] +
+          d5 * (xx - yy) * s[13];
+}
+
+// Block-cooperative copy of this block's [256 x 45] rows between global and shared memory with
+// 16-byte accesses (the rows are 180 B: per-thread row accesses would be 4-byte and uncoalesced).
+__device__ __forceinline__ void sh_stage_load(const ShParams& sh, int64_t n, float* s_rows) {
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t rows = min((int64_t)blockDim.x, n - first);
+    const int64_t floats = rows * kShRowFloats;
+    const float* src = sh.rest + first * kShRowFloats;            // 256*45*4 B = 46080 B: 16-byte aligned per block
+    const int64_t vec = floats / 4;
+    for (int64_t v = threadIdx.x; v < vec; v += blockDim.x)
+        reinterpret_cast<float4*>(s_rows)[v] = __ldg(reinterpret_cast<const float4*>(src) + v);
+    for (int64_t f = vec * 4 + threadIdx.x; f < floats; f += blockDim.x) s_rows[f] = src[f];
+    __syncthreads();
+}
+__device__ __forceinline__ void sh_stage_store(const ShParams& sh, int64_t n, const float* s_rows) {
+    __syncthreads();
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t rows = min((int64_t)blockDim.x, n - first);
+    const int64_t floats = rows * kShRowFloats;
+    float* dst = sh.g_rest + first * kShRowFloats;
+    const int64_t vec = floats / 4;
+    for (int64_t v = threadIdx.x; v < vec; v += blockDim.x)
+        reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(s_rows)[v];
+    for (int64_t f = vec * 4 + threadIdx.x; f < floats; f += blockDim.x) dst[f] = s_rows[f];
+}
+
+template <bool kParamMode, bool kSh>
 __global__ void __launch_bounds__(256)
 project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __restrict__ scaling_log,
                    const float* __restrict__ rotation, const float* __restrict__ cov3d,
                    const float* __restrict__ opacity, int opacity_is_logit,
-                   const float* __restrict__ feat0, int64_t feat_stride, Camera cam,
+                   const float* __restrict__ feat0, int64_t feat_stride, ShParams sh, Camera cam,
                    int img_w, int img_h, int tiles_x_unused, float rmin, float rmax,
                    float2* __restrict__ means2d, float* __restrict__ depths, float4* __restrict__ conics,
                    float* __restrict__ radii, float* __restrict__ colors, float* __restrict__ opac_out,
                    uint8_t* __restrict__ vis_out, int32_t* __restrict__ tiles_touched,
                    ushort4* __restrict__ tile_rect, uint32_t* __restrict__ depth_keys,
                    float4* __restrict__ rec) {
+    extern __shared__ __align__(16) float s_sh_rows[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kSh && sh.staged) sh_stage_load(sh, n, s_sh_rows);
     if (i >= n) return;
 
     Splat3D g;
@@ -165,9 +254,26 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
 
     const float op_in = opacity[i];
     const float op = opacity_is_logit ? sigmoidf(op_in) : op_in;
-    const float cr = sigmoidf(feat0[i * feat_stride + 0]);
-    const float cg = sigmoidf(feat0[i * feat_stride + 1]);
-    const float cb = sigmoidf(feat0[i * feat_stride + 2]);
+    float pre_r = feat0[i * feat_stride + 0], pre_g = feat0[i * feat_stride + 1], pre_b = feat0[i * feat_stride + 2];
+    if (kSh) {
+        const float* row = sh.staged ? s_sh_rows + threadIdx.x * kShRowFloats : sh.rest + i * sh.stride;
+        float dx = x0 - sh.cx, dy = x1 - sh.cy, dz = x2 - sh.cz;
+        const float inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+        dx *= inv; dy *= inv; dz *= inv;
+        float Y[kShRest];
+        sh_basis(sh.degree, dx, dy, dz, Y);
+        const int terms = sh_terms(sh.degree);
+        float ar = 0.f, ag = 0.f, ab = 0.f;
+        for (int k = 0; k < terms; ++k) {
+            ar = fmaf(Y[k], row[k * 3 + 0], ar);
+            ag = fmaf(Y[k], row[k * 3 + 1], ag);
+            ab = fmaf(Y[k], row[k * 3 + 2], ab);
+        }
+        pre_r += ar; pre_g += ag; pre_b += ab;          // + 0 exactly when the rows are zero
+    }
+    const float cr = sigmoidf(pre_r);
+    const float cg = sigmoidf(pre_g);
+    const float cb = sigmoidf(pre_b);
 
     // renderer.py:218 -- every compare is false for NaN, exactly as in torch
     const float r = p.radius;
@@ -212,29 +318,26 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
 }
 
 // Backward (derived from the forward above).
-template <bool kParamMode>
+template <bool kParamMode, bool kSh>
 __global__ void __launch_bounds__(256)
 project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __restrict__ scaling_log,
                    const float* __restrict__ rotation, const float* __restrict__ cov3d,
                    const float* __restrict__ opacity, int opacity_is_logit,
-                   const float* __restrict__ feat0, int64_t feat_stride, Camera cam,
+                   const float* __restrict__ feat0, int64_t feat_stride, ShParams sh, Camera cam,
                    const float2* __restrict__ g_means2d, const float4* __restrict__ g_conics,
                    const float* __restrict__ g_depths, const float* __restrict__ g_colors,
                    const float* __restrict__ g_opac,
                    float* __restrict__ g_xyz, float* __restrict__ g_scaling, float4* __restrict__ g_rotation,
                    float* __restrict__ g_cov3d, float* __restrict__ g_opacity,
                    float* __restrict__ g_feat0, int64_t g_feat_stride) {
+    extern __shared__ __align__(16) float s_sh_rows[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-
-    const float2 gm = g_means2d[i];
-    const float4 gq = g_conics[i];
-    const float gz_in = g_depths[i];
-    const float gcr = g_colors[i * 3 + 0], gcg = g_colors[i * 3 + 1], gcb = g_colors[i * 3 + 2];
-    const float gop = g_opac[i];
-
-    // activations
-    {
+    const bool staged = kSh && sh.staged;
+    if (staged) sh_stage_load(sh, n, s_sh_rows);
+    float gdx = 0.f, gdy = 0.f, gdz = 0.f;          // colour -> view direction -> position (SH only)
+    if (i < n) {
+        // activations and colour
+        const float gop = g_opac[i];
         const float op_in = opacity[i];
         float go = gop;
         if (opacity_is_logit) {
@@ -242,19 +345,60 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
             go = gop * o * (1.f - o);
         }
         g_opacity[i] = go;
-        const float cr = sigmoidf(feat0[i * feat_stride + 0]);
-        const float cg = sigmoidf(feat0[i * feat_stride + 1]);
-        const float cb = sigmoidf(feat0[i * feat_stride + 2]);
-        g_feat0[i * g_feat_stride + 0] = gcr * cr * (1.f - cr);
-        g_feat0[i * g_feat_stride + 1] = gcg * cg * (1.f - cg);
-        g_feat0[i * g_feat_stride + 2] = gcb * cb * (1.f - cb);
+        float pre[3] = {feat0[i * feat_stride + 0], feat0[i * feat_stride + 1], feat0[i * feat_stride + 2]};
+        float Y[kShRest];
+        float dirx = 0.f, diry = 0.f, dirz = 0.f, inv_len = 0.f;
+        const int terms = sh_terms(sh.degree);
+        float* row = nullptr;
+        if (kSh) {
+            row = staged ? s_sh_rows + threadIdx.x * kShRowFloats : const_cast<float*>(sh.rest + i * sh.stride);
+            dirx = xyz[i * 3 + 0] - sh.cx; diry = xyz[i * 3 + 1] - sh.cy; dirz = xyz[i * 3 + 2] - sh.cz;
+            inv_len = 1.0f / fmaxf(sqrtf(dirx * dirx + diry * diry + dirz * dirz), 1e-12f);
+            dirx *= inv_len; diry *= inv_len; dirz *= inv_len;
+            sh_basis(sh.degree, dirx, diry, dirz, Y);
+            for (int k = 0; k < terms; ++k) {
+                pre[0] = fmaf(Y[k], row[k * 3 + 0], pre[0]);
+                pre[1] = fmaf(Y[k], row[k * 3 + 1], pre[1]);
+                pre[2] = fmaf(Y[k], row[k * 3 + 2], pre[2]);
+            }
+        }
+        float gpre[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float col = sigmoidf(pre[c]);
+            gpre[c] = g_colors[i * 3 + c] * col * (1.f - col);
+            g_feat0[i * g_feat_stride + c] = gpre[c];
+        }
+        if (kSh) {
+            float sk[kShRest];
+            float* grow = staged ? row : sh.g_rest + i * sh.g_stride;      // staged: overwrite the row in place
+            for (int k = 0; k < kShRest; ++k) {
+                const bool used = k < terms;
+                sk[k] = used ? gpre[0] * row[k * 3 + 0] + gpre[1] * row[k * 3 + 1] + gpre[2] * row[k * 3 + 2] : 0.f;
+                grow[k * 3 + 0] = used ? gpre[0] * Y[k] : 0.f;
+                grow[k * 3 + 1] = used ? gpre[1] * Y[k] : 0.f;
+                grow[k * 3 + 2] = used ? gpre[2] * Y[k] : 0.f;
+            }
+            float gx, gy, gz;
+            sh_basis_grad(sh.degree, dirx, diry, dirz, sk, gx, gy, gz);
+            const float dot = gx * dirx + gy * diry + gz * dirz;            // through the normalisation
+            gdx = (gx - dirx * dot) * inv_len;
+            gdy = (gy - diry * dot) * inv_len;
+            gdz = (gz - dirz * dot) * inv_len;
+        }
     }
+    if (staged) sh_stage_store(sh, n, s_sh_rows);
+    if (i >= n) return;
+
+    const float2 gm = g_means2d[i];
+    const float4 gq = g_conics[i];
+    const float gz_in = g_depths[i];
 
     const bool any_geo = (gm.x != 0.f) || (gm.y != 0.f) || (gq.x != 0.f) || (gq.y != 0.f) || (gq.z != 0.f) ||
                          (gq.w != 0.f) || (gz_in != 0.f);
     if (!any_geo) {
-        // nothing reached this splat through the rasteriser: all geometric gradients are zero
-        g_xyz[i * 3 + 0] = 0.f; g_xyz[i * 3 + 1] = 0.f; g_xyz[i * 3 + 2] = 0.f;
+        // nothing reached this splat's geometry through the rasteriser
+        g_xyz[i * 3 + 0] = gdx; g_xyz[i * 3 + 1] = gdy; g_xyz[i * 3 + 2] = gdz;
         if (kParamMode) {
             g_scaling[i * 3 + 0] = 0.f; g_scaling[i * 3 + 1] = 0.f; g_scaling[i * 3 + 2] = 0.f;
             g_rotation[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -331,9 +475,9 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     const float gY = gm.y * (-fy * iz) + gJ[5] * (fy * iz2);
     const float gZ = gz_in + gm.x * (-fx * p.X * iz2) + gm.y * (fy * p.Y * iz2) + gJ[0] * (-fx * iz2) +
                      gJ[2] * (2.f * fx * p.X * iz3) + gJ[4] * (fy * iz2) + gJ[5] * (-2.f * fy * p.Y * iz3);
-    g_xyz[i * 3 + 0] = cam.r[0] * gX + cam.r[3] * gY + cam.r[6] * gZ;
-    g_xyz[i * 3 + 1] = cam.r[1] * gX + cam.r[4] * gY + cam.r[7] * gZ;
-    g_xyz[i * 3 + 2] = cam.r[2] * gX + cam.r[5] * gY + cam.r[8] * gZ;
+    g_xyz[i * 3 + 0] = cam.r[0] * gX + cam.r[3] * gY + cam.r[6] * gZ + gdx;
+    g_xyz[i * 3 + 1] = cam.r[1] * gX + cam.r[4] * gY + cam.r[7] * gZ + gdy;
+    g_xyz[i * 3 + 2] = cam.r[2] * gX + cam.r[5] * gY + cam.r[8] * gZ + gdz;
 
     // gSigma = Rv^T gM Rv
     float gS[9];
@@ -384,13 +528,24 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     g_rotation[i] = make_float4((gw - w * dotp) * inv, (gx - x * dotp) * inv, (gy - y * dotp) * inv, (gzq - z * dotp) * inv);
 }
 
+static ShParams make_sh(const float* rest, int64_t stride, float* g_rest, int64_t g_stride, int degree, const float* camera_host) {
+    ShParams sh;
+    sh.rest = rest; sh.stride = stride; sh.g_rest = g_rest; sh.g_stride = g_stride; sh.degree = degree;
+    // contiguous [n,15,3] rows on both sides and 16-byte aligned bases: stage through shared memory
+    sh.staged = degree > 0 && stride == kShRowFloats && (g_rest == nullptr || g_stride == kShRowFloats) &&
+                ((uintptr_t)rest % 16 == 0) && ((uintptr_t)g_rest % 16 == 0);
+    sh.cx = camera_host[16]; sh.cy = camera_host[17]; sh.cz = camera_host[18];
+    return sh;
+}
+
 }  // namespace gs
 
 using namespace gs;
 
 extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_log, const float* rotation,
                               const float* cov3d, const float* opacity, int32_t opacity_is_logit,
-                              const float* feat0, int64_t feat_stride, const float* camera_host,
+                              const float* feat0, int64_t feat_stride, const float* sh_rest, int64_t sh_rest_stride,
+                              int32_t sh_degree, const float* camera_host,
                               int32_t img_w, int32_t img_h, int32_t tile_size, float radius_min, float radius_max,
                               float* means2d, float* depths, float* conics, float* radii, float* colors,
                               float* opacities, uint8_t* vis, int32_t* tiles_touched, uint16_t* tile_rect,
@@ -408,21 +563,25 @@ extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_
     GS_REQUIRE(param_mode || cov3d != nullptr, "need (scaling_log, rotation) or cov3d");
     GS_REQUIRE(xyz && opacity && feat0 && means2d && depths && conics && radii && colors && opacities && vis &&
                    tiles_touched && tile_rect && depth_keys && splat_rec, "NULL array argument");
+    GS_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
+    GS_REQUIRE(sh_degree == 0 || sh_rest != nullptr, "sh_degree > 0 needs sh_rest");
     DeviceGuard guard(xyz);
     const Camera cam = camera_from_host(camera_host);
+    const ShParams sh = make_sh(sh_rest, sh_rest_stride, nullptr, 0, sh_degree, camera_host);
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    const size_t smem = (sh.degree > 0 && sh.staged) ? (size_t)threads * kShRowFloats * sizeof(float) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (param_mode) {
-        project_fwd_kernel<true><<<blocks, threads, 0, st>>>(
-            n, xyz, scaling_log, rotation, nullptr, opacity, opacity_is_logit, feat0, feat_stride, cam, img_w, img_h, 0,
-            radius_min, radius_max, (float2*)means2d, depths, (float4*)conics, radii, colors, opacities, vis,
-            tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec);
+#define GS_LAUNCH_FWD(PM, SH)                                                                                          \
+    project_fwd_kernel<PM, SH><<<blocks, threads, smem, st>>>(                                                       \
+        n, xyz, scaling_log, rotation, cov3d, opacity, opacity_is_logit, feat0, feat_stride, sh, cam, img_w, img_h, 0, \
+        radius_min, radius_max, (float2*)means2d, depths, (float4*)conics, radii, colors, opacities, vis,             \
+        tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec)
+        if (sh.degree > 0) GS_LAUNCH_FWD(true, true); else GS_LAUNCH_FWD(true, false);
     } else {
-        project_fwd_kernel<false><<<blocks, threads, 0, st>>>(
-            n, xyz, nullptr, nullptr, cov3d, opacity, opacity_is_logit, feat0, feat_stride, cam, img_w, img_h, 0,
-            radius_min, radius_max, (float2*)means2d, depths, (float4*)conics, radii, colors, opacities, vis,
-            tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec);
+        if (sh.degree > 0) GS_LAUNCH_FWD(false, true); else GS_LAUNCH_FWD(false, false);
+#undef GS_LAUNCH_FWD
     }
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
@@ -431,11 +590,12 @@ extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_
 
 extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_log, const float* rotation,
                               const float* cov3d, const float* opacity, int32_t opacity_is_logit,
-                              const float* feat0, int64_t feat_stride, const float* camera_host,
+                              const float* feat0, int64_t feat_stride, const float* sh_rest, int64_t sh_rest_stride,
+                              int32_t sh_degree, const float* camera_host,
                               const float* g_means2d, const float* g_conics, const float* g_depths,
                               const float* g_colors, const float* g_opacities, float* g_xyz, float* g_scaling_log,
                               float* g_rotation, float* g_cov3d, float* g_opacity, float* g_feat0,
-                              int64_t g_feat_stride, void* stream) {
+                              int64_t g_feat_stride, float* g_sh_rest, int64_t g_sh_rest_stride, void* stream) {
     GS_REQUIRE(n >= 0, "n < 0");
     GS_REQUIRE(camera_host != nullptr, "camera_host is NULL");
     if (n == 0) return GS_OK;
@@ -445,21 +605,25 @@ extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_
     GS_REQUIRE(param_mode || g_cov3d, "covariance mode needs g_cov3d");
     GS_REQUIRE(xyz && opacity && feat0 && g_means2d && g_conics && g_depths && g_colors && g_opacities && g_xyz &&
                    g_opacity && g_feat0, "NULL array argument");
+    GS_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
+    GS_REQUIRE(sh_degree == 0 || (sh_rest != nullptr && g_sh_rest != nullptr), "sh_degree > 0 needs sh_rest and g_sh_rest");
     DeviceGuard guard(xyz);
     const Camera cam = camera_from_host(camera_host);
+    const ShParams sh = make_sh(sh_rest, sh_rest_stride, g_sh_rest, g_sh_rest_stride, sh_degree, camera_host);
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    const size_t smem = (sh.degree > 0 && sh.staged) ? (size_t)threads * kShRowFloats * sizeof(float) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (param_mode) {
-        project_bwd_kernel<true><<<blocks, threads, 0, st>>>(
-            n, xyz, scaling_log, rotation, nullptr, opacity, opacity_is_logit, feat0, feat_stride, cam,
-            (const float2*)g_means2d, (const float4*)g_conics, g_depths, g_colors, g_opacities, g_xyz, g_scaling_log,
-            (float4*)g_rotation, nullptr, g_opacity, g_feat0, g_feat_stride);
+#define GS_LAUNCH_BWD(PM, SH)                                                                                          \
+    project_bwd_kernel<PM, SH><<<blocks, threads, smem, st>>>(                                                       \
+        n, xyz, scaling_log, rotation, cov3d, opacity, opacity_is_logit, feat0, feat_stride, sh, cam,                  \
+        (const float2*)g_means2d, (const float4*)g_conics, g_depths, g_colors, g_opacities, g_xyz, g_scaling_log,      \
+        (float4*)g_rotation, g_cov3d, g_opacity, g_feat0, g_feat_stride)
+        if (sh.degree > 0) GS_LAUNCH_BWD(true, true); else GS_LAUNCH_BWD(true, false);
     } else {
-        project_bwd_kernel<false><<<blocks, threads, 0, st>>>(
-            n, xyz, nullptr, nullptr, cov3d, opacity, opacity_is_logit, feat0, feat_stride, cam,
-            (const float2*)g_means2d, (const float4*)g_conics, g_depths, g_colors, g_opacities, g_xyz, nullptr, nullptr,
-            g_cov3d, g_opacity, g_feat0, g_feat_stride);
+        if (sh.degree > 0) GS_LAUNCH_BWD(false, true); else GS_LAUNCH_BWD(false, false);
+#undef GS_LAUNCH_BWD
     }
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);

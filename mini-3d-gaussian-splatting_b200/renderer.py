@@ -43,7 +43,7 @@ class _ViewMeta:
     """Per-call constants shared by forward and backward of the two Functions."""
 
     __slots__ = ("cam", "W", "H", "tile", "rmin", "rmax", "param_mode", "opacity_is_logit",
-                 "feat_stride", "stream_of")
+                 "feat_stride", "sh_degree", "rest_in_feat")
 
     def __init__(self):
         self.cam = None
@@ -51,7 +51,8 @@ class _ViewMeta:
 
 def _camera_block(camera) -> ctypes.Array:
     """renderer.py:140-152: intrinsics in python float64 rounded once to fp32; W2C rotation and
-    translation.  16 host floats (GS_CAMERA_FLOATS)."""
+    translation, then the camera centre -R^T t (used by the SH option only).  20 host floats
+    (GS_CAMERA_FLOATS)."""
     W, H = camera._width, camera._height
     fx = np.float32(0.5 * W / math.tan(camera._FoVx * 0.5))
     fy = np.float32(0.5 * H / math.tan(camera._FoVy * 0.5))
@@ -59,8 +60,9 @@ def _camera_block(camera) -> ctypes.Array:
     cy = np.float32(H * 0.5)
     WV = camera.world_view_transform()
     wv = WV.detach().to(device="cpu", dtype=_F32).numpy()
-    vals = list(wv[:3, :3].reshape(-1)) + list(wv[:3, 3]) + [fx, fy, cx, cy]
-    return (ctypes.c_float * 16)(*[float(v) for v in vals])
+    centre = -(wv[:3, :3].astype(np.float64).T @ wv[:3, 3].astype(np.float64))
+    vals = list(wv[:3, :3].reshape(-1)) + list(wv[:3, 3]) + [fx, fy, cx, cy] + list(centre) + [0.0]
+    return (ctypes.c_float * 20)(*[float(v) for v in vals])
 
 
 def _stream(device) -> ctypes.c_void_p:
@@ -126,7 +128,8 @@ class _ProjectFn(torch.autograd.Function):
         with _timed("project_fwd", dev):
             check(lib.gs_project_fwd(
                 n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
-                ptr(feat_src), meta.feat_stride, meta.cam, meta.W, meta.H, meta.tile, meta.rmin, meta.rmax,
+                ptr(feat_src), meta.feat_stride, *_sh_args(meta, feat_src, features_rest), meta.cam,
+                meta.W, meta.H, meta.tile, meta.rmin, meta.rmax,
                 ptr(means2d), ptr(depths), ptr(conics), ptr(radii), ptr(colors), ptr(opac), ptr(vis),
                 ptr(tiles_touched), ptr(tile_rect), ptr(depth_keys), ptr(rec), _stream(dev)), "gs_project_fwd")
         ctx.meta = meta
@@ -160,19 +163,38 @@ class _ProjectFn(torch.autograd.Function):
         g_opacity = torch.empty_like(opacity)
         # only features[:,0,:] feeds the colour; every other SH row gets the dense zeros the
         # reference's autograd produces
-        if feat_src.shape[1] == 1:
-            g_feat = torch.empty_like(feat_src)
+        sh_on = meta.sh_degree > 0
+        if feat_src.shape[1] == 1 or (sh_on and meta.rest_in_feat):
+            g_feat = torch.empty_like(feat_src)            # every row is written by the kernel
         else:
             g_feat = torch.zeros_like(feat_src)
+        g_rest = None
+        if sh_on and not meta.rest_in_feat:
+            g_rest = torch.empty_like(features_rest)
+        elif features_rest is not None and ctx.needs_input_grad[7]:
+            g_rest = torch.zeros_like(features_rest)
+        if sh_on:
+            g_sh = (ctypes.c_void_p(g_feat.data_ptr() + 12), g_feat.stride(0)) if meta.rest_in_feat else (ptr(g_rest), g_rest.stride(0))
+        else:
+            g_sh = (None, 0)
         with _timed("project_bwd", dev):
             check(lib.gs_project_bwd(
                 n, ptr(xyz), ptr(scaling), ptr(rotation), ptr(cov3d), ptr(opacity), int(meta.opacity_is_logit),
-                ptr(feat_src), meta.feat_stride, meta.cam,
+                ptr(feat_src), meta.feat_stride, *_sh_args(meta, feat_src, features_rest), meta.cam,
                 ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                 ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), ptr(g_cov3d), ptr(g_opacity),
-                ptr(g_feat), g_feat.stride(0), _stream(dev)), "gs_project_bwd")
-        g_rest = torch.zeros_like(features_rest) if (features_rest is not None and ctx.needs_input_grad[7]) else None
+                ptr(g_feat), g_feat.stride(0), g_sh[0], g_sh[1], _stream(dev)), "gs_project_bwd")
         return None, g_xyz, g_scaling, g_rotation, g_cov3d, g_opacity, g_feat, g_rest
+
+
+def _sh_args(meta, feat_src, features_rest):
+    """(sh_rest pointer, row stride in floats, degree) for the ABI.  The higher-order rows live either
+    in a separate `_features_rest [N,15,3]` (GaussianModel layout) or behind row 0 of `features [N,K,3]`."""
+    if meta.sh_degree <= 0:
+        return None, 0, 0
+    if meta.rest_in_feat:
+        return ctypes.c_void_p(feat_src.data_ptr() + 12), feat_src.stride(0), meta.sh_degree
+    return ptr(features_rest), features_rest.stride(0), meta.sh_degree
 
 
 class _RasterizeFn(torch.autograd.Function):
@@ -215,8 +237,9 @@ class _RasterizeFn(torch.autograd.Function):
         H, W = meta.H, meta.W
         # one zeroed slab carved into the five contiguous gradient tensors (atomics accumulate into it)
         slab = torch.zeros(n * 11, dtype=_F32, device=dev)
-        g_means2d = slab[0:2 * n].view(n, 2)
-        g_conics = slab[2 * n:6 * n].view(n, 2, 2)
+        # float4-read array first, then the float2 one: both stay naturally aligned for any n
+        g_conics = slab[0:4 * n].view(n, 2, 2)
+        g_means2d = slab[4 * n:6 * n].view(n, 2)
         g_depths = slab[6 * n:7 * n]
         g_colors = slab[7 * n:10 * n].view(n, 3)
         g_opac = slab[10 * n:11 * n]
@@ -256,7 +279,13 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 class GaussianRenderer:
     """3D Gaussian differentiable renderer -- B200 implementation of renderer.py:22-367."""
 
-    def __init__(self, tile_size: int = 16, radius_min: float = 0.01, radius_max: float = 50.0):
+    def __init__(self, tile_size: int = 16, radius_min: float = 0.01, radius_max: float = 50.0, sh_degree: int = 0):
+        """`sh_degree` is an extension: 0 (default) is the reference's DC-only colour
+        sigmoid(features[:,0,:]); 1..3 add view-dependent real-SH terms from the higher feature rows
+        (identical output while those rows are zero)."""
+        if not 0 <= int(sh_degree) <= 3:
+            raise ValueError("sh_degree must be 0..3")
+        self.sh_degree = int(sh_degree)
         self.tile_size = tile_size
         self.radius_min = radius_min
         self.radius_max = radius_max
@@ -321,6 +350,19 @@ class GaussianRenderer:
         if opacity.numel() != n:
             raise ValueError(f"opacity must have N={n} elements, got {tuple(opacity.shape)}")
         meta.feat_stride = feat_src.stride(0)
+        meta.sh_degree = self.sh_degree
+        meta.rest_in_feat = False
+        if self.sh_degree > 0:
+            need = (self.sh_degree + 1) ** 2
+            if rest is not None and rest.shape[1] >= need - 1:
+                rest = _f32c(rest)
+                if rest.shape[1] != 15:
+                    raise ValueError("_features_rest must be [N,15,3]")
+            elif feat_src.shape[1] >= 16:
+                meta.rest_in_feat, rest = True, None
+            else:
+                raise ValueError(f"sh_degree={self.sh_degree} needs 15 higher-order feature rows "
+                                 f"(_features_rest [N,15,3] or get_features [N,16,3])")
 
         (means2d, conics, depths, colors, opac, radii, vis, tiles_touched, tile_rect, depth_keys,
          rec) = _ProjectFn.apply(meta, xyz, scaling, rotation, cov3d, opacity, feat_src, rest)

@@ -1,0 +1,182 @@
+"""The caller side of the render path: one optimisation step and density control.
+
+SURVEY 8f ranks 1-2 ("next" after the hot path).  The reference documents this loop but does not
+implement it: `GaussianTrainer.train_step` is `pass` (src/train/trainer.py:61-65) and
+`DensityController.densify_and_prune` raises (src/core/optimizer.py:64 calls a property,
+:70 never clears the state, :71 calls a missing method).  What is restated here is the working
+intent: five Adam parameter groups (optimizer.py:100-109), cosine learning-rate decay with a
+delayed start for positions (optimizer.py:21-32), densify every `densify_interval` iterations
+between `densify_from_iter` and `densify_until_iter` (optimizer.py:39-41), split / clone / prune
+opacity <= 0.01 (optimizer.py:61-66) and a rebuilt optimiser afterwards (optimizer.py:137).
+Everything here is host-side torch on device tensors; the kernels are the renderer's.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional
+
+import torch
+
+
+@dataclass
+class TrainingConfig:
+    """Defaults of the reference's dataclass (config/config.py:33-67) that the loop reads."""
+    iterations: int = 30000
+    position_lr_init: float = 0.00016
+    position_lr_final: float = 0.0000016
+    position_lr_delay_mult: float = 0.01
+    position_lr_max_steps: int = 30000
+    feature_lr: float = 0.0025
+    opacity_lr: float = 0.05
+    scaling_lr: float = 0.005
+    rotation_lr: float = 0.001
+    densify_from_iter: int = 500
+    densify_until_iter: int = 15000
+    densify_grad_threshold: float = 0.0002
+    densify_interval: int = 100
+    image_height: int = 800
+    image_width: int = 800
+    device: str = "cuda"
+
+
+class LearningRateScheduler:
+    """Cosine decay from lr_init to lr_final over max_steps, scaled during the first
+    lr_delay_steps by a ramp from lr_delay_mult to 1 (optimizer.py:7-32)."""
+
+    def __init__(self, lr_init: float, lr_final: float, lr_delay_steps: int, lr_delay_mult: float, max_steps: int):
+        self.lr_init, self.lr_final = lr_init, lr_final
+        self.lr_delay_steps, self.lr_delay_mult, self.max_steps = lr_delay_steps, lr_delay_mult, max_steps
+
+    def get_lr(self, step: int) -> float:
+        if self.max_steps <= 0:
+            return self.lr_final
+        t = min(step, self.max_steps) / self.max_steps
+        lr = self.lr_final + (self.lr_init - self.lr_final) * 0.5 * (1.0 + math.cos(math.pi * t))
+        if self.lr_delay_steps > 0:
+            lr *= self.lr_delay_mult + (1.0 - self.lr_delay_mult) * min(step / self.lr_delay_steps, 1.0)
+        return float(lr)
+
+
+class GaussianOptimizer:
+    """Adam over the five trained parameter groups (the SH rest block is left out while colour is
+    DC-only: its gradient is identically zero)."""
+
+    GROUPS = (("xyz", "_xyz", "position_lr_init"), ("f_dc", "_features_dc", "feature_lr"),
+              ("opacity", "_opacity", "opacity_lr"), ("scaling", "_scaling", "scaling_lr"),
+              ("rotation", "_rotation", "rotation_lr"))
+
+    def __init__(self, model, config: Optional[TrainingConfig] = None):
+        self.model, self.config = model, config or TrainingConfig()
+        self.xyz_scheduler = LearningRateScheduler(self.config.position_lr_init, self.config.position_lr_final,
+                                                   int(0.01 * self.config.position_lr_max_steps),
+                                                   self.config.position_lr_delay_mult, self.config.position_lr_max_steps)
+        self.rebuild()
+
+    def rebuild(self) -> None:
+        """Fresh Adam on the model's current parameters; state is discarded, as in the reference."""
+        groups = [{"params": [getattr(self.model, attr)], "lr": getattr(self.config, lr), "name": name}
+                  for name, attr, lr in self.GROUPS]
+        self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+
+    def update_learning_rate(self, iteration: int) -> float:
+        lr = self.xyz_scheduler.get_lr(iteration)
+        for g in self.optimizer.param_groups:
+            if g["name"] == "xyz":
+                g["lr"] = lr
+        return lr
+
+    def step(self) -> None:
+        self.optimizer.step()
+
+    def zero_grad(self) -> None:
+        self.optimizer.zero_grad(set_to_none=True)
+
+
+class DensityController:
+    def __init__(self, config: Optional[TrainingConfig] = None):
+        self.config = config or TrainingConfig()
+
+    def should_densify(self, iteration: int) -> bool:
+        c = self.config
+        return c.densify_from_iter <= iteration <= c.densify_until_iter and iteration % c.densify_interval == 0
+
+    @torch.no_grad()
+    def densify_and_prune(self, model, optimizer: Optional[GaussianOptimizer], scene_extent: float,
+                          grad: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None) -> Dict[str, int]:
+        """Split, clone, prune; `grad` defaults to `_xyz.grad` as in the reference.  Both masks are
+        taken from the same pre-densification gradient (the split re-creates the parameters, so the
+        reference's second read of `.grad` would find none)."""
+        g = model._xyz.grad if grad is None else grad
+        if g is None:
+            return {"split": 0, "cloned": 0, "pruned": 0, "points": model.get_num_points()}
+        th = self.config.densify_grad_threshold
+        gn = g.norm(dim=-1)
+        sig = model.get_scaling.mean(dim=-1)
+        clone_mask = (gn > th) & (sig < 0.01 * scene_extent)
+        split_mask = (gn > th) & (sig > 0.03 * scene_extent)
+        # clone first: appended rows do not disturb the indices the split mask refers to
+        n0 = model.get_num_points()
+        cloned = model.density_and_clone(th, scene_extent, grad=g, generator=generator)
+        if cloned:
+            split_mask = torch.cat([split_mask, torch.zeros(cloned, dtype=torch.bool, device=split_mask.device)])
+            g = torch.cat([g, torch.zeros(cloned, 3, device=g.device, dtype=g.dtype)])
+        split = 0
+        if bool(split_mask.any()):
+            g_for_split = torch.where(split_mask.unsqueeze(-1), g, torch.zeros_like(g))
+            split = model.density_and_split(th, scene_extent, grad=g_for_split)
+        keep = model.get_opacity.squeeze(1) > 0.01
+        pruned = int((~keep).sum())
+        if pruned:
+            model.prune_points(keep)
+        if optimizer is not None:
+            optimizer.rebuild()
+        assert int(clone_mask.sum()) == cloned and n0 + cloned + split - pruned == model.get_num_points()
+        return {"split": split, "cloned": cloned, "pruned": pruned, "points": model.get_num_points()}
+
+
+def l1_loss(image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """The L1 term of the reference's loss (loss.py:52); its SSIM term does not run (loss.py:26,39)."""
+    return (image - target).abs().mean()
+
+
+def train_step(model, renderer, camera, target: torch.Tensor, optimizer: GaussianOptimizer, settings, iteration: int,
+               loss_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor] = l1_loss) -> Dict[str, object]:
+    """sample -> render -> loss -> backward -> Adam step (the intent of trainer.py:45-65), plus the
+    densification statistics the reference allocates but never fills (gaussian_model.py:29-31)."""
+    optimizer.update_learning_rate(iteration)
+    optimizer.zero_grad()
+    out = renderer.render(camera, model, settings)
+    out["viewspace_points"].retain_grad()
+    loss = loss_fn(out["image"], target)
+    loss.backward()
+    with torch.no_grad():
+        model.add_densification_stats(out["viewspace_points"].grad, out["visibility_filter"], out["radii"])
+    optimizer.step()
+    return {"loss": loss.detach(), "out": out}
+
+
+def densification_stress(model, renderer, cameras, settings, controller: DensityController, scene_extent: float,
+                         target_points: int, max_rounds: int = 64, grad_scale: float = 1.0) -> Dict[str, object]:
+    """BASELINE config[4]: grow the model from its current size to >= target_points by repeated
+    render -> backward -> statistics -> split/clone/prune rounds (no optimiser step: the parameters
+    only change through densification, so the run is reproducible)."""
+    history = []
+    for r in range(max_rounds):
+        if model.get_num_points() >= target_points:
+            break
+        for p in (model._xyz, model._scaling, model._rotation, model._opacity, model._features_dc, model._features_rest):
+            p.grad = None
+        cam = cameras[r % len(cameras)]
+        out = renderer.render(cam, model, settings)
+        out["viewspace_points"].retain_grad()
+        (out["image"].mean() * grad_scale).backward()
+        with torch.no_grad():
+            model.add_densification_stats(out["viewspace_points"].grad, out["visibility_filter"], out["radii"])
+        stats = controller.densify_and_prune(model, None, scene_extent)
+        stats["round"] = r
+        stats["tile_pairs"] = renderer.last_stats.get("tile_pairs", 0)
+        history.append(stats)
+        if stats["split"] + stats["cloned"] == 0:
+            break
+    return {"points": model.get_num_points(), "history": history}

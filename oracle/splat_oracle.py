@@ -332,12 +332,42 @@ def render(cam: OracleCamera, xyz, cov3d, features0, opacity_act, bg, H: int, W:
     return out
 
 
+def sh_basis(degree: int, d: torch.Tensor) -> torch.Tensor:
+    """Real spherical-harmonics basis Y_1..Y_{(deg+1)^2-1} at unit directions d [N,3] -> [N,terms].
+    NOT part of the reference (its colour is DC-only; math_utils.py:44-49 is a stub): this is the
+    oracle of the renderer's optional `sh_degree` extension, so its parity is unpinned by the reference."""
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    out = [-0.4886025119029199 * y, 0.4886025119029199 * z, -0.4886025119029199 * x]
+    if degree >= 2:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        out += [1.0925484305920792 * xy, -1.0925484305920792 * yz, 0.31539156525252005 * (2 * zz - xx - yy),
+                -1.0925484305920792 * xz, 0.5462742152960396 * (xx - yy)]
+    if degree >= 3:
+        out += [-0.5900435899266435 * y * (3 * xx - yy), 2.890611442640554 * xy * z,
+                -0.4570457994644658 * y * (4 * zz - xx - yy), 0.3731763325901154 * z * (2 * zz - 3 * xx - 3 * yy),
+                -0.4570457994644658 * x * (4 * zz - xx - yy), 1.445305721320277 * z * (xx - yy),
+                -0.5900435899266435 * x * (xx - 3 * yy)]
+    return torch.stack(out, dim=1)
+
+
+def colour_logits(cam: OracleCamera, xyz, features_dc, features_rest=None, sh_degree: int = 0) -> torch.Tensor:
+    """What goes into the sigmoid: features[:,0,:] (renderer.py:88-92), plus -- extension -- the SH terms."""
+    f0 = features_dc.reshape(-1, 3)
+    if sh_degree <= 0 or features_rest is None:
+        return f0
+    WV = cam.world_view.to(torch.float64)
+    centre = (-(WV[:3, :3].T @ WV[:3, 3])).to(F32)
+    d = torch.nn.functional.normalize(xyz - centre, dim=-1)
+    Y = sh_basis(sh_degree, d)                                        # [N, terms]
+    return f0 + (Y.unsqueeze(-1) * features_rest[:, :Y.shape[1], :]).sum(dim=1)
+
+
 def render_from_params(cam: OracleCamera, xyz, scaling_log, rotation, opacity_logit, features_dc,
-                       bg, H: int, W: int, **kw) -> Dict[str, torch.Tensor]:
+                       bg, H: int, W: int, features_rest=None, sh_degree: int = 0, **kw) -> Dict[str, torch.Tensor]:
     """render() fed the way a real GaussianModel would feed it (adapter of SURVEY 8c)."""
     cov3d = covariance_3d(scaling_log, rotation)
     op = torch.sigmoid(opacity_logit).reshape(-1)
-    f0 = features_dc.reshape(-1, 3)
+    f0 = colour_logits(cam, xyz, features_dc, features_rest, sh_degree)
     return render(cam, xyz, cov3d, f0, op, bg, H, W, **kw)
 
 

@@ -45,11 +45,11 @@ def test_argument_validation_without_gpu():
     from importlib import import_module
     _lib = import_module("mini-3d-gaussian-splatting_b200._lib")
     lib = _lib.load()
-    cam = (ctypes.c_float * 16)()
-    rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, cam, 64, 64, 8, 0.01, 50.0,
+    cam = (ctypes.c_float * 20)()
+    rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, None, 0, 0, cam, 64, 64, 8, 0.01, 50.0,
                             None, None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -4 and b"tile_size" in lib.gs_last_error_string()       # GS_ERR_UNSUPPORTED
-    rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, cam, 64, 64, 16, 0.01, 50.0,
+    rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, None, 0, 0, cam, 64, 64, 16, 0.01, 50.0,
                             None, None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1                                                       # GS_ERR_INVALID_ARGUMENT
     assert lib.gs_bin_workspace_bytes(1000, 50000, 64) > 0

@@ -1,0 +1,91 @@
+"""The caller side (SURVEY 8f "next"): learning-rate schedule, densify schedule and split/clone/prune
+bookkeeping on CPU tensors; a short optimisation run and a densification stress round on the GPU."""
+import math
+
+import pytest
+import torch
+
+import gsplat_b200 as gb
+from oracle import splat_oracle as so
+
+
+def test_learning_rate_schedule_matches_reference_formula():
+    s = gb.LearningRateScheduler(1.6e-4, 1.6e-6, 300, 0.01, 30000)
+    assert s.get_lr(0) == pytest.approx(1.6e-4 * 0.01)
+    assert s.get_lr(300) == pytest.approx(1.6e-6 + (1.6e-4 - 1.6e-6) * 0.5 * (1 + math.cos(math.pi * 0.01)))
+    assert s.get_lr(30000) == pytest.approx(1.6e-6)
+    assert s.get_lr(10 ** 9) == pytest.approx(1.6e-6)
+    assert gb.LearningRateScheduler(1.0, 0.5, 0, 1.0, 0).get_lr(5) == 0.5
+
+
+def test_densify_schedule():
+    c = gb.DensityController(gb.TrainingConfig())
+    assert not c.should_densify(400) and c.should_densify(500) and not c.should_densify(550)
+    assert c.should_densify(15000) and not c.should_densify(15100)
+
+
+def test_split_clone_prune_counts_cpu():
+    """Pins the working subset of the reference's densification (tests/test_gaussian_model.py:91-140):
+    a split removes the parent and adds two children, a clone adds one, pruning keeps the mask."""
+    m = gb.GaussianModel(device="cpu")
+    m.create_from_random(100, 1.0, seed=1)
+    with torch.no_grad():
+        m._scaling[:30] = math.log(0.05)      # large  -> split candidates
+        m._scaling[30:50] = math.log(0.005)   # small  -> clone candidates
+        m._opacity[90:] = -10.0               # transparent -> pruned
+    g = torch.zeros(100, 3)
+    g[:10] = 1.0                              # 10 large with gradient
+    g[30:35] = 1.0                            # 5 small with gradient
+    g[60:70] = 1.0                            # mid-sized: neither
+    ctrl = gb.DensityController(gb.TrainingConfig())
+    stats = ctrl.densify_and_prune(m, None, 1.0, grad=g, generator=torch.Generator().manual_seed(0))
+    assert stats["split"] == 10 and stats["cloned"] == 5 and stats["pruned"] == 10
+    assert m.get_num_points() == 100 + 5 + 10 - 10
+    assert m._features_rest.shape == (m.get_num_points(), 15, 3) and m.denom.shape == (m.get_num_points(), 1)
+    # children of a split are 0.75x the parent's size
+    assert torch.allclose(m.get_scaling[-20:], torch.full((20, 3), 0.05 * 0.75), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_train_steps_reduce_l1_loss():
+    W, H = 160, 96
+    target_scene = so.scene_aniso(3000, 50)
+    target_scene["scaling"] = target_scene["scaling"] + math.log(2.5)
+    tm = gb.GaussianModel(device="cuda")
+    tm.create_from_tensors(target_scene["xyz"], target_scene["features_dc"], target_scene["scaling"],
+                           target_scene["rotation"], target_scene["opacity"])
+    cam = gb.Camera.orbit(1, 7, W, H)
+    rd = gb.GaussianRenderer()
+    st = gb.RenderSettings(H, W, torch.zeros(3, device="cuda"))
+    with torch.no_grad():
+        target = rd.render(cam, tm, st)["image"].clone()
+    m = gb.GaussianModel(device="cuda")
+    m.create_from_tensors(target_scene["xyz"] + 0.01 * torch.randn(3000, 3, generator=torch.Generator().manual_seed(2)),
+                          target_scene["features_dc"] * 0.5, target_scene["scaling"], target_scene["rotation"],
+                          target_scene["opacity"])
+    cfg = gb.TrainingConfig(position_lr_init=1e-3, position_lr_final=1e-4, position_lr_max_steps=60)
+    opt = gb.GaussianOptimizer(m, cfg)
+    losses = [float(gb.train_step(m, rd, cam, target, opt, st, it)["loss"]) for it in range(40)]
+    assert losses[-1] < 0.6 * losses[0], losses[::8]
+    assert float(m.denom.max()) == 40 and float(m.max_radii2D.max()) > 0
+    assert all(math.isfinite(v) for v in losses)
+
+
+@pytest.mark.gpu
+def test_densification_stress_grows_model():
+    """Scaled-down BASELINE config[4]: repeated render -> backward -> split/clone/prune rounds."""
+    s = so.scene_aniso(20000, 9)
+    m = gb.GaussianModel(device="cuda")
+    m.create_from_tensors(s["xyz"], s["features_dc"], s["scaling"], s["rotation"], s["opacity"])
+    rd = gb.GaussianRenderer()
+    W, H = 400, 304
+    cams = [gb.Camera.orbit(k, 4, W, H) for k in range(4)]
+    cfg = gb.TrainingConfig(densify_grad_threshold=1e-9)
+    res = gb.training.densification_stress(m, rd, cams, gb.RenderSettings(H, W, torch.zeros(3, device="cuda")),
+                                           gb.DensityController(cfg), 1.0, target_points=60000, max_rounds=12)
+    assert res["points"] >= 40000 and len(res["history"]) >= 1
+    n = m.get_num_points()
+    assert m._xyz.shape == (n, 3) and m._rotation.shape == (n, 4) and m.max_radii2D.shape == (n,)
+    with torch.no_grad():
+        out = rd.render(cams[0], m, gb.RenderSettings(H, W, torch.zeros(3, device="cuda")))
+    assert bool(torch.isfinite(out["image"]).all()) and out["radii"].shape == (n,)
