@@ -208,7 +208,9 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def loss_fn(out, w):
-        return (w[0] * out["image"]).sum() + (w[1] * out["alpha"]).sum() + 0.1 * (w[2] * out["depth"]).sum()
+        # SURVEY 8d loss  sum(w_img*image) + sum(w_a*alpha) + 0.1*sum(w_d*depth), written as three dot products
+        return (torch.dot(w[0].view(-1), out["image"].view(-1)) + torch.dot(w[1].view(-1), out["alpha"].view(-1))
+                + 0.1 * torch.dot(w[2].view(-1), out["depth"].view(-1)))
 
     def step_device():
         res = mv.multiview_step(model, rd, [cam], settings, lambda out, vid: loss_fn(out, w_dev), buffer=buf, reduce=world > 1)
@@ -216,13 +218,25 @@ def main():
 
     cam_wv_host = cam.world_view_transform().clone().pin_memory()
     stage = [torch.empty_like(t, device=dev) for t in w_host]
+    copy_stream = torch.cuda.Stream(device=dev)
 
     def step_e2e():
-        # this step's host inputs: camera pose + loss weights (the "ground truth" side of the step)
+        # this step's host inputs: camera pose + loss weights (the "ground truth" side of the step).  The
+        # 41.5 MB weight upload runs on a copy stream under projection / binning / compositing; the loss
+        # waits for it.  Every step ends with a host read of the loss, so the staging buffers are free again.
         c = gb.Camera(WIDTH, HEIGHT, cam._FoVx, cam._FoVy, world_view=cam_wv_host)   # pose: 64 B, passed by value to the kernels
-        for s_, h_ in zip(stage, w_host):
-            s_.copy_(h_, non_blocking=True)
-        res = mv.multiview_step(model, rd, [c], settings, lambda out, vid: loss_fn(out, stage), buffer=buf, reduce=world > 1)
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(copy_stream):
+            for s_, h_ in zip(stage, w_host):
+                s_.copy_(h_, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(copy_stream)
+
+        def loss_after_upload(out, vid):
+            torch.cuda.current_stream(dev).wait_event(uploaded)
+            return loss_fn(out, stage)
+
+        res = mv.multiview_step(model, rd, [c], settings, loss_after_upload, buffer=buf, reduce=world > 1)
         return float(res["losses"][0].item())                    # D2H read of the step's result
 
     def barrier():

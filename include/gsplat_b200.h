@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 6
+#define GS_ABI_VERSION 7
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -113,7 +113,14 @@ int gs_project_fwd(int64_t n,
  *   g_opacity [n] (w.r.t. the logit when opacity_is_logit, else w.r.t. the activated value);
  *   g_feat0: row i channel c at g_feat0[i*g_feat_stride + c]; with sh_degree 0 the other feature
  *            rows are the caller's to zero (the reference yields zeros there -- SURVEY 3.2);
- *   g_sh_rest (sh_degree > 0): all 15 higher-order rows are written (rows beyond the degree as 0). */
+ *   g_sh_rest (sh_degree > 0): all 15 higher-order rows are written (rows beyond the degree as 0).
+ * accumulate != 0: every result above is ADDED to what its buffer holds instead of written -- the
+ *   multi-view step accumulates the views' parameter gradients straight into one flat buffer
+ *   (replaces the `.grad +=` that autograd would otherwise run per tensor).
+ * stat_* (all NULL, or all non-NULL, each [n]): densification statistics fused into this pass; for
+ *   every splat with stat_vis[i] != 0:  stat_grad_norm[i] += |g_means2d[i]|, stat_count[i] += 1,
+ *   stat_max_radii[i] = max(stat_max_radii[i], stat_radii[i]).  These are the buffers the reference
+ *   allocates as xyz_gradient_accum / denom / max_radii2D (gaussian_model.py:29-31). */
 int gs_project_bwd(int64_t n,
                    const float* xyz,
                    const float* scaling_log, const float* rotation,
@@ -127,6 +134,9 @@ int gs_project_bwd(int64_t n,
                    float* g_xyz, float* g_scaling_log, float* g_rotation, float* g_cov3d,
                    float* g_opacity, float* g_feat0, int64_t g_feat_stride,
                    float* g_sh_rest, int64_t g_sh_rest_stride,
+                   int32_t accumulate,
+                   const float* stat_radii, const uint8_t* stat_vis,
+                   float* stat_grad_norm, float* stat_count, float* stat_max_radii,
                    void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 LIB_NAME = "libgsplat_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
@@ -25,7 +25,7 @@ SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gs_project_bwd": (c_int32, [c_int64, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P, c_int64, c_int32, _P,
                                   _P, _P, _P, _P, _P,
-                                  _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P]),
+                                  _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "gs_bin_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
     "gs_bin_prepare": (c_int32, [c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
     "gs_bin_sort": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,

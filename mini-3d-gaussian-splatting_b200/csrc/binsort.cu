@@ -117,22 +117,33 @@ entry_keys_kernel(int64_t d, const uint32_t* __restrict__ sorted_tile_keys, cons
 // ------------------------------------------------------------------------------------------------
 // Stable counting sort on the tile id (default path).
 //
-// The pairs are produced in depth order, so grouping them by tile while KEEPING that order is all
-// the second sort has to do.  Depth ranks are cut into chunks of kChunk consecutive ranks; one warp
-// walks its chunk in rank order with a shared-memory counter per tile, which gives every pair its
-// position among the chunk's pairs of the same tile (`local`) and, at the end, the chunk's row of the
-// [chunks x tiles] count table.  A column scan over chunks plus a scan over tiles turns the table
-// into base offsets, and a fully parallel pass scatters:  pos = tile_start[t] + base[chunk][t] + local.
-// Order within a tile is (chunk, local) = depth rank: stable by construction, no atomics, no
-// comparison of keys.  Traffic ~ 6 B/pair + the table, against ~36 B/pair for two radix passes.
+// The pairs exist only implicitly: depth rank j touches the tiles of tile_rect[sorted_ids[j]], and
+//   pos(j, t) = tile_start[t] + #{ j' < j : rect(j') contains t }.
+// Depth ranks are cut into chunks of kChunk consecutive ranks, chunks into super-chunks of kSuper.
+//   1. chunk_walk_kernel    one warp per chunk walks its ranks IN ORDER with a uint8 running counter per
+//                           tile in shared memory: local[pair] = pairs of the same tile earlier in the
+//                           chunk (uint8, written coalesced), counts[chunk][t] (uint8 row) at the end
+//   2. column_prefix_kernel base16[chunk][t] = pairs of tile t in earlier chunks of the same super-chunk
+//                           (uint16), super_tot[super][t]
+//   3. super_prefix_kernel + tile_scan_kernel   super_tab -> exclusive prefix over supers; tile_start / tile_ranges
+//   4. scatter_kernel       fully parallel, in rank order (so the 4-byte stores of neighbouring list
+//                           entries reach L2 close together and merge before they are written back):
+//                           entry_ids[tile_start + super_tab + base16 + local] = id
+// Order within a tile is (super, chunk, local) = depth rank: stable by construction, no comparison of
+// keys, no atomics.  A fused walk+scatter (stores issued from the sequential walk) was measured and
+// rejected: every chunk then writes its share of a list sector at an unrelated time, L2 evicts the
+// partial sectors, and DRAM traffic grows from ~0.3 GB to ~0.95 GB (profiles/r1_v5_binning.md).
 // ------------------------------------------------------------------------------------------------
-constexpr int kChunk = 512;            // depth ranks per chunk (one warp); counts fit uint16
+constexpr int kChunk = 255;            // depth ranks per chunk: running counts fit uint8
+constexpr int kSuper = 256;            // chunks per super-chunk: 65 280 ranks, prefix fits uint16
+constexpr int kRowAlign = 128;         // table rows padded to 128 tiles (uchar4 / ushort4 / uint4 accesses)
+static_assert(kChunk <= 255 && (kSuper - 1) * kChunk <= 65535, "counter widths");
 
 // A splat's tile rectangle packed for warp broadcast: origin tile index, width, tile count, and the
 // reciprocal used to split k into (row, col) without an integer division in the inner loop.
 struct RectDesc {
     int origin;        // ty0 * tiles_x + tx0
-    int w_cnt;         // width | count << 12   (count <= 4095 on this path, else `big`)
+    int w_cnt;         // width | count << 12   (count capped at kMaxFastCount; larger rectangles take the slow loop)
     unsigned inv;      // 65536 / w + 1
 };
 constexpr int kMaxFastCount = 4095;
@@ -156,40 +167,50 @@ __device__ __forceinline__ int tile_of(int k, int origin, int w, unsigned inv, i
     return origin + row * tiles_x + (k - row * w);
 }
 
+// 1. ordered walk.  The warp takes its ranks 32 at a time (one rectangle descriptor per lane, ids and
+// rectangles software-pipelined one and two blocks ahead) and passes them IN RANK ORDER through the
+// shared-memory counters; lane k serves tiles k, k+32, ... of the current rectangle.  A splat's tiles
+// are distinct, so a splat never conflicts with itself; __syncwarp orders consecutive splats.
 __global__ void __launch_bounds__(32)
-chunk_count_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
-                   const ushort4* __restrict__ tile_rect, int tiles_x, int num_tiles,
-                   uint16_t* __restrict__ local_pos, uint16_t* __restrict__ counts /* [chunks][tiles] */) {
-    extern __shared__ uint16_t s_cnt[];
+chunk_walk_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
+                  const ushort4* __restrict__ tile_rect, int tiles_x, int row_tiles,
+                  uint8_t* __restrict__ local_pos, uint8_t* __restrict__ counts /* [chunks][row_tiles] */) {
+    extern __shared__ uint32_t s_words[];
+    uint8_t* s_cnt = reinterpret_cast<uint8_t*>(s_words);
     const int lane = threadIdx.x;
     const int64_t chunk = blockIdx.x;
-    for (int t = lane; t < num_tiles; t += 32) s_cnt[t] = 0;
+    const int words = row_tiles >> 2;
+    for (int w = lane; w < words; w += 32) s_words[w] = 0u;
     __syncwarp();
     const int64_t j_begin = chunk * kChunk;
     const int64_t j_end = min(j_begin + (int64_t)kChunk, num_sorted);
+    const ushort4 kNoRect = make_ushort4(1, 1, 0, 0);                  // width 0 -> count 0
+    int id_cur = (j_begin + lane < j_end) ? sorted_ids[j_begin + lane] : -1;
+    int id_nxt = (j_begin + 32 + lane < j_end) ? sorted_ids[j_begin + 32 + lane] : -1;
+    ushort4 r_cur = id_cur >= 0 ? tile_rect[id_cur] : kNoRect;
     const int64_t off_base = offsets[j_begin];
-    uint16_t* lp = local_pos + off_base;
+    int off_cur = (j_begin + lane < j_end) ? (int)(offsets[j_begin + lane] - off_base) : 0;
+    uint8_t* lp = local_pos + off_base;
     for (int64_t j0 = j_begin; j0 < j_end; j0 += 32) {
-        const int64_t j = j0 + lane;
-        int off = 0, cnt = 0;
+        const ushort4 r_nxt = id_nxt >= 0 ? tile_rect[id_nxt] : kNoRect;
+        const int id_nn = (j0 + 64 + lane < j_end) ? sorted_ids[j0 + 64 + lane] : -1;
+        const int off_nxt = (j0 + 32 + lane < j_end) ? (int)(offsets[j0 + 32 + lane] - off_base) : 0;
+        int cnt = 0;
         RectDesc d = {0, 1, 65537u};
-        if (j < j_end) {
-            off = (int)(offsets[j] - off_base);
-            d = make_desc(tile_rect[sorted_ids[j]], tiles_x, cnt);
-        }
+        if (id_cur >= 0) d = make_desc(r_cur, tiles_x, cnt);
         const int limit = (int)min((int64_t)32, j_end - j0);
 #pragma unroll 4
         for (int l = 0; l < limit; ++l) {
-            const int s_off = __shfl_sync(0xffffffffu, off, l);
+            const int s_off = __shfl_sync(0xffffffffu, off_cur, l);
             const int s_origin = __shfl_sync(0xffffffffu, d.origin, l);
             const int s_wc = __shfl_sync(0xffffffffu, d.w_cnt, l);
             const unsigned s_inv = __shfl_sync(0xffffffffu, d.inv, l);
-            const int s_w = s_wc & 0xfff, s_cnt_l = s_wc >> 12;
-            if (s_cnt_l < kMaxFastCount) {
-                for (int k = lane; k < s_cnt_l; k += 32) {          // a splat's tiles are distinct: no conflicts
+            const int s_w = s_wc & 0xfff, s_n = s_wc >> 12;
+            if (s_n < kMaxFastCount) {
+                for (int k = lane; k < s_n; k += 32) {
                     const int t = tile_of(k, s_origin, s_w, s_inv, tiles_x);
-                    const uint16_t c = s_cnt[t];
-                    s_cnt[t] = (uint16_t)(c + 1);
+                    const uint8_t c = s_cnt[t];
+                    s_cnt[t] = (uint8_t)(c + 1);
                     lp[s_off + k] = c;
                 }
             } else {                                                 // huge rectangle: exact division
@@ -197,129 +218,202 @@ chunk_count_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, c
                 for (int k = lane; k < full; k += 32) {
                     const int row = k / s_w;
                     const int t = s_origin + row * tiles_x + (k - row * s_w);
-                    const uint16_t c = s_cnt[t];
-                    s_cnt[t] = (uint16_t)(c + 1);
+                    const uint8_t c = s_cnt[t];
+                    s_cnt[t] = (uint8_t)(c + 1);
                     lp[s_off + k] = c;
                 }
             }
-            __syncwarp();                                            // next splat (next depth rank) sees these counts
+            __syncwarp();                                            // the next rank sees these counts
         }
+        id_cur = id_nxt; r_cur = r_nxt; id_nxt = id_nn; off_cur = off_nxt;
     }
-    uint16_t* row = counts + chunk * (int64_t)num_tiles;
-    for (int t = lane; t < num_tiles; t += 32) row[t] = s_cnt[t];
+    uint32_t* row = reinterpret_cast<uint32_t*>(counts + chunk * row_tiles);
+    for (int w = lane; w < words; w += 32) row[w] = s_words[w];
 }
 
-// Exclusive scan over chunks for every tile.  Block = 32 tiles x 32 contiguous chunk segments.
+// 2. exclusive prefix over the chunks of one super-chunk, for 128 tiles per block.
+// Block = 32 lanes (4 tiles each) x 32 segments of kSuper/32 chunks.
+constexpr int kSegChunks = kSuper / 32;
 __global__ void __launch_bounds__(1024)
-column_scan_kernel(int num_chunks, int num_tiles, const uint16_t* __restrict__ counts, uint32_t* __restrict__ base,
-                   uint32_t* __restrict__ tile_total) {
-    __shared__ uint32_t s_sum[32][33];
-    const int tl = threadIdx.x, seg = threadIdx.y;
-    const int t = blockIdx.x * 32 + tl;
-    const int per = (num_chunks + 31) / 32;
-    const int c0 = seg * per, c1 = min(c0 + per, num_chunks);
-    uint32_t sum = 0;
-    if (t < num_tiles)
-        for (int c = c0; c < c1; ++c) sum += counts[(int64_t)c * num_tiles + t];
-    s_sum[seg][tl] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int s2 = 0; s2 < seg; ++s2) run += s_sum[s2][tl];
-    if (t < num_tiles) {
-        if (seg == 31) tile_total[t] = run + sum;
-        for (int c = c0; c < c1; ++c) {
-            const int64_t at = (int64_t)c * num_tiles + t;
-            base[at] = run;
-            run += counts[at];
-        }
+column_prefix_kernel(int num_chunks, int row_tiles, const uint8_t* __restrict__ counts, uint16_t* __restrict__ base16,
+                     uint32_t* __restrict__ super_tot /* [supers][row_tiles] */) {
+    __shared__ uint4 s_seg[32][33];
+    const int lane = threadIdx.x, seg = threadIdx.y;
+    const int t4 = (blockIdx.x * 32 + lane) * 4;
+    const int sup = blockIdx.y;
+    const int c0 = sup * kSuper + seg * kSegChunks;
+    uchar4 v[kSegChunks];
+    uint4 sum = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 0; q < kSegChunks; ++q) {
+        v[q] = make_uchar4(0, 0, 0, 0);
+        if (c0 + q < num_chunks) v[q] = *reinterpret_cast<const uchar4*>(counts + (int64_t)(c0 + q) * row_tiles + t4);
+        sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w;
     }
+    s_seg[seg][lane] = sum;
+    __syncthreads();
+    uint4 run = make_uint4(0, 0, 0, 0);
+    for (int s2 = 0; s2 < seg; ++s2) {
+        const uint4 o = s_seg[s2][lane];
+        run.x += o.x; run.y += o.y; run.z += o.z; run.w += o.w;
+    }
+#pragma unroll
+    for (int q = 0; q < kSegChunks; ++q) {
+        if (c0 + q < num_chunks)
+            *reinterpret_cast<ushort4*>(base16 + (int64_t)(c0 + q) * row_tiles + t4) =
+                make_ushort4((unsigned short)run.x, (unsigned short)run.y, (unsigned short)run.z, (unsigned short)run.w);
+        run.x += v[q].x; run.y += v[q].y; run.z += v[q].z; run.w += v[q].w;
+    }
+    if (seg == 31) *reinterpret_cast<uint4*>(super_tot + (int64_t)sup * row_tiles + t4) = run;
 }
 
-// Exclusive scan over tiles -> tile_ranges [begin,end) and tile_start.  One block of 1024 threads:
-// per-thread serial sums, warp-shuffle scan, one cross-warp scan.
+// 3a. per tile: exclusive prefix over the super-chunks (in place) and the tile's total.  One thread per
+// tile, coalesced across the block; the loads of a column are independent and stay in flight together.
+__global__ void __launch_bounds__(128)
+super_prefix_kernel(int row_tiles, int num_supers, uint32_t* __restrict__ super_tab, uint32_t* __restrict__ tile_total) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= row_tiles) return;
+    uint32_t run = 0u;
+    int s = 0;
+    for (; s + 8 <= num_supers; s += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = super_tab[(int64_t)(s + q) * row_tiles + t];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            super_tab[(int64_t)(s + q) * row_tiles + t] = run;
+            run += v[q];
+        }
+    }
+    for (; s < num_supers; ++s) {
+        const uint32_t v = super_tab[(int64_t)s * row_tiles + t];
+        super_tab[(int64_t)s * row_tiles + t] = run;
+        run += v;
+    }
+    tile_total[t] = run;
+}
+
+// 3b. exclusive scan over tiles -> tile_start and tile_ranges [begin,end).  One block of 1024 threads.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int num_tiles, const uint32_t* __restrict__ tile_total, uint32_t* __restrict__ tile_start,
                  int32_t* __restrict__ ranges) {
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (num_tiles + 1023) / 1024;
-    const int t0 = tid * per, t1 = min(t0 + per, num_tiles);
-    uint32_t sum = 0;
-    for (int t = t0; t < t1; ++t) sum += tile_total[t];
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    if (lane == 31) s_warp[wid] = inc;
+    if (tid == 0) s_carry = 0u;
     __syncthreads();
-    if (wid == 0) {
-        uint32_t w = s_warp[lane], winc = w;
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int t = base + tid;
+        const uint32_t v = t < num_tiles ? tile_total[t] : 0u;
+        uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += v;
+            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
         }
-        s_warp[lane] = winc - w;            // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    uint32_t run = s_warp[wid] + inc - sum;
-    for (int t = t0; t < t1; ++t) {
-        const uint32_t c = tile_total[t];
-        tile_start[t] = run;
-        ranges[2 * t] = c ? (int32_t)run : 0;      // empty tiles report (0,0), as the radix path does
-        ranges[2 * t + 1] = c ? (int32_t)(run + c) : 0;
-        run += c;
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t w = s_warp[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += x;
+            }
+            s_warp[lane] = winc - w;            // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t begin = s_carry + s_warp[wid] + inc - v;
+        if (t < num_tiles) {
+            tile_start[t] = begin;
+            ranges[2 * t] = v ? (int32_t)begin : 0;       // empty tiles report (0,0), as the radix path does
+            ranges[2 * t + 1] = v ? (int32_t)(begin + v) : 0;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = begin + v;
+        __syncthreads();
     }
 }
 
-// One thread per depth rank: its tiles' loads are independent of each other, so they pipeline.
+// 4. parallel scatter in rank order.  One warp per 32 consecutive ranks; for each rank the lanes serve
+// its tiles side by side, so the table reads of a rectangle row and the local_pos read are coalesced.
+// Measured floor: the 26 M four-byte stores land in 26 M different 32-byte sectors and the kernel runs
+// at ~110 G store sectors/s whatever the load side does (batching the loads 4 ranks deep, 2x the
+// instructions in flight, changed nothing -- profiles/r1_v5_binning.md).
 __global__ void __launch_bounds__(256)
 scatter_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
-               const ushort4* __restrict__ tile_rect, int tiles_x, int num_tiles,
-               const uint16_t* __restrict__ local_pos, const uint32_t* __restrict__ base,
-               const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ depth_keys,
-               int32_t* __restrict__ entry_ids, uint64_t* __restrict__ entry_keys) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= num_sorted) return;
-    const int id = sorted_ids[j];
-    const int64_t off = offsets[j];
-    const ushort4 r = tile_rect[id];
-    const uint32_t* base_row = base + (j / kChunk) * (int64_t)num_tiles;
-    const uint16_t* lp = local_pos + off;
-    const uint64_t dkey = entry_keys ? (uint64_t)depth_keys[id] : 0ull;
-    int k = 0;
-    for (int ty = r.y; ty <= (int)r.w; ++ty) {
-        const int trow = ty * tiles_x;
+               const ushort4* __restrict__ tile_rect, int tiles_x, int row_tiles,
+               const uint8_t* __restrict__ local_pos, const uint16_t* __restrict__ base16,
+               const uint32_t* __restrict__ super_base, const uint32_t* __restrict__ tile_start,
+               const uint32_t* __restrict__ depth_keys, int32_t* __restrict__ entry_ids,
+               uint64_t* __restrict__ entry_keys) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (j0 >= num_sorted) return;
+    const int64_t j = j0 + lane;
+    int id = 0, cnt = 0;
+    long long off = 0;
+    RectDesc d = {0, 1, 65537u};
+    uint32_t dk = 0u;
+    if (j < num_sorted) {
+        id = sorted_ids[j];
+        off = offsets[j];
+        d = make_desc(tile_rect[id], tiles_x, cnt);
+        if (entry_keys) dk = depth_keys[id];
+    }
+    const int limit = (int)min((int64_t)32, num_sorted - j0);
 #pragma unroll 4
-        for (int tx = r.x; tx <= (int)r.z; ++tx, ++k) {
-            const int t = trow + tx;
-            const uint32_t pos = tile_start[t] + base_row[t] + (uint32_t)lp[k];
-            entry_ids[pos] = id;
-            if (entry_keys) entry_keys[pos] = ((uint64_t)(uint32_t)t << 32) | dkey;
+    for (int l = 0; l < limit; ++l) {
+        const int s_id = __shfl_sync(0xffffffffu, id, l);
+        const long long s_off = __shfl_sync(0xffffffffu, off, l);
+        const int s_origin = __shfl_sync(0xffffffffu, d.origin, l);
+        const int s_wc = __shfl_sync(0xffffffffu, d.w_cnt, l);
+        const unsigned s_inv = __shfl_sync(0xffffffffu, d.inv, l);
+        const int full = __shfl_sync(0xffffffffu, cnt, l);
+        const uint64_t s_dk = (uint64_t)__shfl_sync(0xffffffffu, dk, l);
+        const int s_w = s_wc & 0xfff;
+        const int64_t chunk = (j0 + l) / kChunk;
+        const uint16_t* b16 = base16 + chunk * row_tiles;
+        const uint32_t* sb = super_base + (chunk / kSuper) * row_tiles;
+        const uint8_t* lp = local_pos + s_off;
+        const bool fast = full <= kMaxFastCount;
+        for (int k = lane; k < full; k += 32) {
+            int t;
+            if (fast) {
+                t = tile_of(k, s_origin, s_w, s_inv, tiles_x);
+            } else {
+                const int row = k / s_w;
+                t = s_origin + row * tiles_x + (k - row * s_w);
+            }
+            const uint32_t pos = tile_start[t] + sb[t] + (uint32_t)b16[t] + (uint32_t)lp[k];
+            entry_ids[pos] = s_id;
+            if (entry_keys) entry_keys[pos] = ((uint64_t)(uint32_t)t << 32) | s_dk;
         }
     }
 }
 
 struct CountLayout {
-    int64_t counts, base, local_pos, tile_total, tile_start, total;
-    int num_chunks;
+    int64_t counts, base16, super_tab, tile_total, tile_start, local_pos, total;
+    int num_chunks, num_supers, row_tiles;
 };
 static CountLayout count_layout(int64_t num_sorted_cap, int64_t d, int32_t num_tiles) {
     CountLayout L;
     L.num_chunks = (int)((num_sorted_cap + kChunk - 1) / kChunk);
     if (L.num_chunks < 1) L.num_chunks = 1;
+    L.num_supers = (L.num_chunks + kSuper - 1) / kSuper;
+    L.row_tiles = (int)align_up(num_tiles, kRowAlign);
     int64_t o = 0;
-    L.counts = o;     o += align_up((int64_t)L.num_chunks * num_tiles * 2, 256);
-    L.base = o;       o += align_up((int64_t)L.num_chunks * num_tiles * 4, 256);
-    L.local_pos = o;  o += align_up(d * 2, 256);
-    L.tile_total = o; o += align_up((int64_t)num_tiles * 4, 256);
-    L.tile_start = o; o += align_up((int64_t)num_tiles * 4, 256);
+    L.counts = o;     o += align_up((int64_t)L.num_chunks * L.row_tiles, 256);
+    L.base16 = o;     o += align_up((int64_t)L.num_chunks * L.row_tiles * 2, 256);
+    L.super_tab = o;  o += align_up((int64_t)L.num_supers * L.row_tiles * 4, 256);
+    L.tile_total = o; o += align_up((int64_t)L.row_tiles * 4, 256);
+    L.tile_start = o; o += align_up((int64_t)L.row_tiles * 4, 256);
+    L.local_pos = o;  o += align_up(d, 256);
     L.total = o;
     return L;
 }
-constexpr int kMaxCountingTiles = 100000;      // 2 B of shared memory per tile for the chunk counters
+constexpr int kMaxCountingTiles = 200000;      // 1 B of shared memory per tile for the running counters
 
 static int tile_bits(int32_t num_tiles) {
     int bits = 1;
@@ -449,25 +543,34 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
             return GS_ERR_WORKSPACE_TOO_SMALL;
         }
         char* wsc = (char*)workspace;
-        uint16_t* counts = (uint16_t*)(wsc + C.counts);
-        uint32_t* base = (uint32_t*)(wsc + C.base);
-        uint16_t* local_pos = (uint16_t*)(wsc + C.local_pos);
+        uint8_t* counts = (uint8_t*)(wsc + C.counts);
+        uint16_t* base16 = (uint16_t*)(wsc + C.base16);
+        uint32_t* super_tab = (uint32_t*)(wsc + C.super_tab);
         uint32_t* tile_total = (uint32_t*)(wsc + C.tile_total);
         uint32_t* tile_start = (uint32_t*)(wsc + C.tile_start);
-        const size_t smem = (size_t)num_tiles * sizeof(uint16_t);
-        if (smem > 48 * 1024) GS_CUDA_TRY(cudaFuncSetAttribute(chunk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        chunk_count_kernel<<<C.num_chunks, 32, smem, st>>>(num_sorted, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x,
-                                                          num_tiles, local_pos, counts);
+        uint8_t* local_pos = (uint8_t*)(wsc + C.local_pos);
+        const size_t smem_walk = (size_t)C.row_tiles;
+        if (smem_walk > 48 * 1024) GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_walk));
+        // one warp + row_tiles bytes per CTA: residency is bounded by shared memory, so ask for the largest carve-out
+        GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        chunk_walk_kernel<<<C.num_chunks, 32, smem_walk, st>>>(num_sorted, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x,
+                                                              C.row_tiles, local_pos, counts);
         GS_CUDA_TRY(cudaGetLastError());
-        column_scan_kernel<<<(num_tiles + 31) / 32, dim3(32, 32), 0, st>>>(C.num_chunks, num_tiles, counts, base, tile_total);
+        column_prefix_kernel<<<dim3(C.row_tiles / kRowAlign, C.num_supers), dim3(32, 32), 0, st>>>(
+            C.num_chunks, C.row_tiles, counts, base16, super_tab);
+        GS_CUDA_TRY(cudaGetLastError());
+        super_prefix_kernel<<<C.row_tiles / 128, 128, 0, st>>>(C.row_tiles, C.num_supers, super_tab, tile_total);
         GS_CUDA_TRY(cudaGetLastError());
         tile_scan_kernel<<<1, 1024, 0, st>>>(num_tiles, tile_total, tile_start, tile_ranges);
         GS_CUDA_TRY(cudaGetLastError());
-        scatter_kernel<<<(unsigned)((num_sorted + 255) / 256), 256, 0, st>>>(
-            num_sorted, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, num_tiles, local_pos, base, tile_start,
-            depth_keys, entry_ids, entry_keys);
+        {
+            const int64_t warps = (num_sorted + 31) / 32;
+            scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+                num_sorted, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, local_pos, base16,
+                super_tab, tile_start, depth_keys, entry_ids, entry_keys);
+        }
         GS_CUDA_TRY(cudaGetLastError());
-        count_launches(4);
+        count_launches(5);
         return GS_OK;
     }
     const SortLayout L = sort_layout(d, num_tiles);

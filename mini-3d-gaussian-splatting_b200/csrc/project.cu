@@ -212,17 +212,37 @@ __device__ __forceinline__ void sh_stage_load(const ShParams& sh, int64_t n, flo
     for (int64_t f = vec * 4 + threadIdx.x; f < floats; f += blockDim.x) s_rows[f] = src[f];
     __syncthreads();
 }
-__device__ __forceinline__ void sh_stage_store(const ShParams& sh, int64_t n, const float* s_rows) {
+__device__ __forceinline__ void sh_stage_store(const ShParams& sh, int64_t n, const float* s_rows, bool accumulate) {
     __syncthreads();
     const int64_t first = (int64_t)blockIdx.x * blockDim.x;
     const int64_t rows = min((int64_t)blockDim.x, n - first);
     const int64_t floats = rows * kShRowFloats;
     float* dst = sh.g_rest + first * kShRowFloats;
     const int64_t vec = floats / 4;
-    for (int64_t v = threadIdx.x; v < vec; v += blockDim.x)
-        reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(s_rows)[v];
-    for (int64_t f = vec * 4 + threadIdx.x; f < floats; f += blockDim.x) dst[f] = s_rows[f];
+    for (int64_t v = threadIdx.x; v < vec; v += blockDim.x) {
+        float4 val = reinterpret_cast<const float4*>(s_rows)[v];
+        if (accumulate) {
+            const float4 old = reinterpret_cast<const float4*>(dst)[v];
+            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+        }
+        reinterpret_cast<float4*>(dst)[v] = val;
+    }
+    for (int64_t f = vec * 4 + threadIdx.x; f < floats; f += blockDim.x) dst[f] = accumulate ? dst[f] + s_rows[f] : s_rows[f];
 }
+
+// Densification statistics fused into the projection backward (the reference allocates these
+// buffers but never fills them: gaussian_model.py:29-31).  For every visible splat:
+//   grad_norm[i] += |dL/d means2D[i]|,  count[i] += 1,  max_radii[i] = max(max_radii[i], radii[i]).
+struct DensifyStats {
+    const float* radii;
+    const uint8_t* vis;
+    float* grad_norm;
+    float* count;
+    float* max_radii;
+};
+
+// results are written, or added to what the buffer holds (multi-view gradient accumulation)
+__device__ __forceinline__ void emit(float* p, float v, bool accumulate) { *p = accumulate ? *p + v : v; }
 
 template <bool kParamMode, bool kSh>
 __global__ void __launch_bounds__(256)
@@ -329,10 +349,11 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
                    const float* __restrict__ g_opac,
                    float* __restrict__ g_xyz, float* __restrict__ g_scaling, float4* __restrict__ g_rotation,
                    float* __restrict__ g_cov3d, float* __restrict__ g_opacity,
-                   float* __restrict__ g_feat0, int64_t g_feat_stride) {
+                   float* __restrict__ g_feat0, int64_t g_feat_stride, int accumulate_i, DensifyStats stats) {
     extern __shared__ __align__(16) float s_sh_rows[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool staged = kSh && sh.staged;
+    const bool acc = accumulate_i != 0;
     if (staged) sh_stage_load(sh, n, s_sh_rows);
     float gdx = 0.f, gdy = 0.f, gdz = 0.f;          // colour -> view direction -> position (SH only)
     if (i < n) {
@@ -344,7 +365,7 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
             const float o = sigmoidf(op_in);
             go = gop * o * (1.f - o);
         }
-        g_opacity[i] = go;
+        emit(g_opacity + i, go, acc);
         float pre[3] = {feat0[i * feat_stride + 0], feat0[i * feat_stride + 1], feat0[i * feat_stride + 2]};
         float Y[kShRest];
         float dirx = 0.f, diry = 0.f, dirz = 0.f, inv_len = 0.f;
@@ -367,7 +388,7 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
         for (int c = 0; c < 3; ++c) {
             const float col = sigmoidf(pre[c]);
             gpre[c] = g_colors[i * 3 + c] * col * (1.f - col);
-            g_feat0[i * g_feat_stride + c] = gpre[c];
+            emit(g_feat0 + i * g_feat_stride + c, gpre[c], acc);
         }
         if (kSh) {
             float sk[kShRest];
@@ -375,9 +396,10 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
             for (int k = 0; k < kShRest; ++k) {
                 const bool used = k < terms;
                 sk[k] = used ? gpre[0] * row[k * 3 + 0] + gpre[1] * row[k * 3 + 1] + gpre[2] * row[k * 3 + 2] : 0.f;
-                grow[k * 3 + 0] = used ? gpre[0] * Y[k] : 0.f;
-                grow[k * 3 + 1] = used ? gpre[1] * Y[k] : 0.f;
-                grow[k * 3 + 2] = used ? gpre[2] * Y[k] : 0.f;
+                // the staged row is private scratch (added to global memory by sh_stage_store)
+                emit(grow + k * 3 + 0, used ? gpre[0] * Y[k] : 0.f, acc && !staged);
+                emit(grow + k * 3 + 1, used ? gpre[1] * Y[k] : 0.f, acc && !staged);
+                emit(grow + k * 3 + 2, used ? gpre[2] * Y[k] : 0.f, acc && !staged);
             }
             float gx, gy, gz;
             sh_basis_grad(sh.degree, dirx, diry, dirz, sk, gx, gy, gz);
@@ -387,10 +409,15 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
             gdz = (gz - dirz * dot) * inv_len;
         }
     }
-    if (staged) sh_stage_store(sh, n, s_sh_rows);
+    if (staged) sh_stage_store(sh, n, s_sh_rows, acc);
     if (i >= n) return;
 
     const float2 gm = g_means2d[i];
+    if (stats.grad_norm != nullptr && stats.vis[i]) {
+        stats.grad_norm[i] += sqrtf(gm.x * gm.x + gm.y * gm.y);
+        stats.count[i] += 1.0f;
+        stats.max_radii[i] = fmaxf(stats.max_radii[i], stats.radii[i]);
+    }
     const float4 gq = g_conics[i];
     const float gz_in = g_depths[i];
 
@@ -398,6 +425,10 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
                          (gq.w != 0.f) || (gz_in != 0.f);
     if (!any_geo) {
         // nothing reached this splat's geometry through the rasteriser
+        if (acc) {
+            if (kSh) { g_xyz[i * 3 + 0] += gdx; g_xyz[i * 3 + 1] += gdy; g_xyz[i * 3 + 2] += gdz; }
+            return;
+        }
         g_xyz[i * 3 + 0] = gdx; g_xyz[i * 3 + 1] = gdy; g_xyz[i * 3 + 2] = gdz;
         if (kParamMode) {
             g_scaling[i * 3 + 0] = 0.f; g_scaling[i * 3 + 1] = 0.f; g_scaling[i * 3 + 2] = 0.f;
@@ -475,9 +506,9 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     const float gY = gm.y * (-fy * iz) + gJ[5] * (fy * iz2);
     const float gZ = gz_in + gm.x * (-fx * p.X * iz2) + gm.y * (fy * p.Y * iz2) + gJ[0] * (-fx * iz2) +
                      gJ[2] * (2.f * fx * p.X * iz3) + gJ[4] * (fy * iz2) + gJ[5] * (-2.f * fy * p.Y * iz3);
-    g_xyz[i * 3 + 0] = cam.r[0] * gX + cam.r[3] * gY + cam.r[6] * gZ + gdx;
-    g_xyz[i * 3 + 1] = cam.r[1] * gX + cam.r[4] * gY + cam.r[7] * gZ + gdy;
-    g_xyz[i * 3 + 2] = cam.r[2] * gX + cam.r[5] * gY + cam.r[8] * gZ + gdz;
+    emit(g_xyz + i * 3 + 0, cam.r[0] * gX + cam.r[3] * gY + cam.r[6] * gZ + gdx, acc);
+    emit(g_xyz + i * 3 + 1, cam.r[1] * gX + cam.r[4] * gY + cam.r[7] * gZ + gdy, acc);
+    emit(g_xyz + i * 3 + 2, cam.r[2] * gX + cam.r[5] * gY + cam.r[8] * gZ + gdz, acc);
 
     // gSigma = Rv^T gM Rv
     float gS[9];
@@ -488,7 +519,7 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     }
     if (!kParamMode) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) g_cov3d[i * 9 + k] = gS[k];
+        for (int k = 0; k < 9; ++k) emit(g_cov3d + i * 9 + k, gS[k], acc);
         return;
     }
     // Sigma = R D R^T, D = diag(sig^2)
@@ -510,13 +541,13 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         // (R^T gS R)_kk
-        float acc = 0.f;
+        float racc = 0.f;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc += R[r * 3 + k] * gS[r * 3 + c] * R[c * 3 + k];
+            for (int c = 0; c < 3; ++c) racc += R[r * 3 + k] * gS[r * 3 + c] * R[c * 3 + k];
         // d(sig^2)/d(log-scale) = 2 sig^2
-        g_scaling[i * 3 + k] = 2.f * acc * g.sig[k] * g.sig[k];
+        emit(g_scaling + i * 3 + k, 2.f * racc * g.sig[k] * g.sig[k], acc);
     }
     const float w = g.qh[0], x = g.qh[1], y = g.qh[2], z = g.qh[3];
     const float gw = 2.f * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]);
@@ -525,7 +556,12 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     const float gzq = 2.f * (-2.f * z * gR[0] - w * gR[1] + x * gR[2] + w * gR[3] - 2.f * z * gR[4] + y * gR[5] + x * gR[6] + y * gR[7]);
     const float dotp = w * gw + x * gx + y * gy + z * gzq;
     const float inv = 1.0f / g.qn;
-    g_rotation[i] = make_float4((gw - w * dotp) * inv, (gx - x * dotp) * inv, (gy - y * dotp) * inv, (gzq - z * dotp) * inv);
+    float4 gq_out = make_float4((gw - w * dotp) * inv, (gx - x * dotp) * inv, (gy - y * dotp) * inv, (gzq - z * dotp) * inv);
+    if (acc) {
+        const float4 old = g_rotation[i];
+        gq_out.x += old.x; gq_out.y += old.y; gq_out.z += old.z; gq_out.w += old.w;
+    }
+    g_rotation[i] = gq_out;
 }
 
 static ShParams make_sh(const float* rest, int64_t stride, float* g_rest, int64_t g_stride, int degree, const float* camera_host) {
@@ -595,7 +631,9 @@ extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_
                               const float* g_means2d, const float* g_conics, const float* g_depths,
                               const float* g_colors, const float* g_opacities, float* g_xyz, float* g_scaling_log,
                               float* g_rotation, float* g_cov3d, float* g_opacity, float* g_feat0,
-                              int64_t g_feat_stride, float* g_sh_rest, int64_t g_sh_rest_stride, void* stream) {
+                              int64_t g_feat_stride, float* g_sh_rest, int64_t g_sh_rest_stride, int32_t accumulate,
+                              const float* stat_radii, const uint8_t* stat_vis, float* stat_grad_norm,
+                              float* stat_count, float* stat_max_radii, void* stream) {
     GS_REQUIRE(n >= 0, "n < 0");
     GS_REQUIRE(camera_host != nullptr, "camera_host is NULL");
     if (n == 0) return GS_OK;
@@ -607,6 +645,10 @@ extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_
                    g_opacity && g_feat0, "NULL array argument");
     GS_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
     GS_REQUIRE(sh_degree == 0 || (sh_rest != nullptr && g_sh_rest != nullptr), "sh_degree > 0 needs sh_rest and g_sh_rest");
+    const bool want_stats = stat_grad_norm != nullptr;
+    GS_REQUIRE(!want_stats || (stat_radii && stat_vis && stat_count && stat_max_radii),
+               "densification statistics need radii, vis, grad_norm, count and max_radii together");
+    const DensifyStats stats = {stat_radii, stat_vis, want_stats ? stat_grad_norm : nullptr, stat_count, stat_max_radii};
     DeviceGuard guard(xyz);
     const Camera cam = camera_from_host(camera_host);
     const ShParams sh = make_sh(sh_rest, sh_rest_stride, g_sh_rest, g_sh_rest_stride, sh_degree, camera_host);
@@ -619,7 +661,7 @@ extern "C" int gs_project_bwd(int64_t n, const float* xyz, const float* scaling_
     project_bwd_kernel<PM, SH><<<blocks, threads, smem, st>>>(                                                       \
         n, xyz, scaling_log, rotation, cov3d, opacity, opacity_is_logit, feat0, feat_stride, sh, cam,                  \
         (const float2*)g_means2d, (const float4*)g_conics, g_depths, g_colors, g_opacities, g_xyz, g_scaling_log,      \
-        (float4*)g_rotation, g_cov3d, g_opacity, g_feat0, g_feat_stride)
+        (float4*)g_rotation, g_cov3d, g_opacity, g_feat0, g_feat_stride, accumulate, stats)
         if (sh.degree > 0) GS_LAUNCH_BWD(true, true); else GS_LAUNCH_BWD(true, false);
     } else {
         if (sh.degree > 0) GS_LAUNCH_BWD(false, true); else GS_LAUNCH_BWD(false, false);

@@ -38,15 +38,17 @@ class FlatGradBuffer:
         n = params[0].shape[0]
         sizes = [p.numel() for p in params]
         self.n = n
-        self.param_elems = sum(sizes)
-        self.flat = torch.zeros(self.param_elems + 2 * n, dtype=torch.float32, device=params[0].device)
-        self.views = []
-        off = 0
-        for p, sz in zip(params, sizes):
-            self.views.append(self.flat[off:off + sz].view_as(p))
-            off += sz
+        # every segment starts on a 16-byte boundary (the kernels accumulate into them with float4 accesses)
+        pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731
+        offs, off = [], 0
+        for sz in sizes:
+            offs.append(off)
+            off = pad4(off + sz)
+        self.param_elems = off
+        self.flat = torch.zeros(self.param_elems + 2 * pad4(n), dtype=torch.float32, device=params[0].device)
+        self.views = [self.flat[o:o + sz].view_as(p) for p, o, sz in zip(params, offs, sizes)]
         self.grad_norm_sum = self.flat[off:off + n]
-        self.vis_count = self.flat[off + n:off + 2 * n]
+        self.vis_count = self.flat[off + pad4(n):off + pad4(n) + n]
         self.max_radii = torch.zeros(n, dtype=torch.float32, device=params[0].device)
 
     def install(self) -> None:
@@ -83,14 +85,25 @@ def multiview_step(model, renderer, cameras: Sequence, settings, loss_fn: Callab
     buf.install()
     ids = list(view_ids) if view_ids is not None else list(range(len(cameras)))
     losses = []
-    for cam, vid in zip(cameras, ids):
-        out = renderer.render(cam, model, settings)
-        out["viewspace_points"].retain_grad()
-        loss = loss_fn(out, vid)
-        loss.backward()
-        with torch.no_grad():
-            buf.add_view_stats(out["viewspace_points"].grad, out["visibility_filter"], out["radii"].detach())
-        losses.append(loss.detach())
+    # B200 renderer: the projection backward adds gradients and statistics into `buf` itself
+    # (gs_project_bwd accumulate + stat_*); any other renderer goes through autograd accumulation.
+    fused = hasattr(renderer, "accumulate_into") and getattr(renderer, "sh_degree", 0) == 0
+    if fused:
+        with renderer.accumulate_into(buf):
+            for cam, vid in zip(cameras, ids):
+                out = renderer.render(cam, model, settings)
+                loss = loss_fn(out, vid)
+                loss.backward()
+                losses.append(loss.detach())
+    else:
+        for cam, vid in zip(cameras, ids):
+            out = renderer.render(cam, model, settings)
+            out["viewspace_points"].retain_grad()
+            loss = loss_fn(out, vid)
+            loss.backward()
+            with torch.no_grad():
+                buf.add_view_stats(out["viewspace_points"].grad, out["visibility_filter"], out["radii"].detach())
+            losses.append(loss.detach())
     if reduce:
         buf.all_reduce(group)
     return {"buffer": buf, "losses": losses}

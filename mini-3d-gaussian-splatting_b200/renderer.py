@@ -43,10 +43,11 @@ class _ViewMeta:
     """Per-call constants shared by forward and backward of the two Functions."""
 
     __slots__ = ("cam", "W", "H", "tile", "rmin", "rmax", "param_mode", "opacity_is_logit",
-                 "feat_stride", "sh_degree", "rest_in_feat")
+                 "feat_stride", "sh_degree", "rest_in_feat", "sink")
 
     def __init__(self):
         self.cam = None
+        self.sink = None
 
 
 def _camera_block(camera) -> ctypes.Array:
@@ -134,6 +135,8 @@ class _ProjectFn(torch.autograd.Function):
                 ptr(tiles_touched), ptr(tile_rect), ptr(depth_keys), ptr(rec), _stream(dev)), "gs_project_fwd")
         ctx.meta = meta
         ctx.save_for_backward(xyz, scaling, rotation, cov3d, opacity, feat_src, features_rest)
+        if meta.sink is not None:
+            ctx.stat_inputs = (radii, vis)        # plain (non-graph) outputs: read by the fused statistics
         vis_b = vis.view(torch.bool)
         ctx.mark_non_differentiable(radii, vis_b, tiles_touched, tile_rect, depth_keys, rec)
         return means2d, conics, depths, colors, opac, radii, vis_b, tiles_touched, tile_rect, depth_keys, rec
@@ -156,6 +159,22 @@ class _ProjectFn(torch.autograd.Function):
         g_depths = dense(g_depths, n)
         g_colors = dense(g_colors, n, 3)
         g_opac = dense(g_opac, n)
+        sink = meta.sink
+        if sink is not None:
+            # multi-view accumulation: add straight into the caller's flat gradient buffer and fill the
+            # densification statistics in the same pass; autograd then has nothing left to accumulate
+            g_xyz, g_feat, g_scaling, g_rotation, g_opacity = sink.views
+            radii, vis = ctx.stat_inputs
+            with _timed("project_bwd", dev):
+                check(lib.gs_project_bwd(
+                    n, ptr(xyz), ptr(scaling), ptr(rotation), None, ptr(opacity), 1,
+                    ptr(feat_src), meta.feat_stride, None, 0, 0, meta.cam,
+                    ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
+                    ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), None, ptr(g_opacity),
+                    ptr(g_feat), 3, None, 0, 1,
+                    ptr(radii), ptr(vis), ptr(sink.grad_norm_sum), ptr(sink.vis_count), ptr(sink.max_radii),
+                    _stream(dev)), "gs_project_bwd")
+            return (None,) * 8
         g_xyz = torch.empty_like(xyz)
         g_scaling = torch.empty_like(scaling) if meta.param_mode else None
         g_rotation = torch.empty_like(rotation) if meta.param_mode else None
@@ -183,7 +202,8 @@ class _ProjectFn(torch.autograd.Function):
                 ptr(feat_src), meta.feat_stride, *_sh_args(meta, feat_src, features_rest), meta.cam,
                 ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                 ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), ptr(g_cov3d), ptr(g_opacity),
-                ptr(g_feat), g_feat.stride(0), g_sh[0], g_sh[1], _stream(dev)), "gs_project_bwd")
+                ptr(g_feat), g_feat.stride(0), g_sh[0], g_sh[1], 0, None, None, None, None, None,
+                _stream(dev)), "gs_project_bwd")
         return None, g_xyz, g_scaling, g_rotation, g_cov3d, g_opacity, g_feat, g_rest
 
 
@@ -292,7 +312,29 @@ class GaussianRenderer:
         self.device = torch.device("cuda")
         self.last_stats: Dict[str, int] = {}
         self.bin_algo = 0          # GS_BIN_AUTO; 1 = counting sort, 2 = library radix sort (cross-check)
+        # Optional gradient sink (multiview.FlatGradBuffer): while set, the projection backward adds the
+        # parameter gradients and the densification statistics straight into it (see `accumulate_into`).
+        self.grad_sink = None
         _lib.load()   # fail at construction, not at first render, if the extension is missing
+
+    def accumulate_into(self, sink):
+        """Context manager: renders made inside it back-propagate by ADDING into `sink` -- an object
+        with `n`, `views` (gradient buffers for _xyz, _features_dc, _scaling, _rotation, _opacity, in
+        that order) and `grad_norm_sum / vis_count / max_radii` [N] -- instead of through autograd's
+        per-tensor `.grad` accumulation.  Only GaussianModel-shaped inputs with DC-only colour take this
+        path; anything else back-propagates as usual."""
+        renderer = self
+
+        class _Scope:
+            def __enter__(self_inner):
+                self_inner.prev = renderer.grad_sink
+                renderer.grad_sink = sink
+                return sink
+
+            def __exit__(self_inner, *exc):
+                renderer.grad_sink = self_inner.prev
+                return False
+        return _Scope()
 
     # ------------------------------------------------------------------------------------
     def render(self, camera, gaussians, settings: RenderSettings) -> Dict[str, torch.Tensor]:
@@ -363,6 +405,11 @@ class GaussianRenderer:
             else:
                 raise ValueError(f"sh_degree={self.sh_degree} needs 15 higher-order feature rows "
                                  f"(_features_rest [N,15,3] or get_features [N,16,3])")
+
+        sink = self.grad_sink
+        if (sink is not None and meta.param_mode and self.sh_degree == 0 and sink.n == n and feat_src.shape[1] == 1
+                and torch.is_grad_enabled()):
+            meta.sink = sink
 
         (means2d, conics, depths, colors, opac, radii, vis, tiles_touched, tile_rect, depth_keys,
          rec) = _ProjectFn.apply(meta, xyz, scaling, rotation, cov3d, opacity, feat_src, rest)

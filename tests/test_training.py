@@ -89,3 +89,42 @@ def test_densification_stress_grows_model():
     with torch.no_grad():
         out = rd.render(cams[0], m, gb.RenderSettings(H, W, torch.zeros(3, device="cuda")))
     assert bool(torch.isfinite(out["image"]).all()) and out["radii"].shape == (n,)
+
+
+@pytest.mark.gpu
+def test_fused_gradient_sink_equals_autograd_accumulation():
+    """multiview_step on the B200 renderer adds parameter gradients and densification statistics inside
+    gs_project_bwd (accumulate + stat_*); it must equal autograd's `.grad +=` plus add_view_stats."""
+    mv = gb.multiview
+    s = so.scene_aniso(4001, 31)                 # odd count: float4 accumulations stay aligned
+    s["scaling"] = s["scaling"] + math.log(2.5)
+    W, H = 176, 112
+    cams = [gb.Camera.orbit(k, 5, W, H) for k in (0, 2, 3)]
+    st = gb.RenderSettings(H, W, torch.tensor([0.1, 0.0, 0.2], device="cuda"))
+    wts = [tuple(t.cuda() for t in so.loss_weights(H, W, seed=10 + k)) for k in range(3)]
+
+    def loss_fn(out, vid):
+        return so.weighted_loss(out, wts[vid])
+
+    def run(fused: bool):
+        m = gb.GaussianModel(device="cuda")
+        m.create_from_tensors(s["xyz"], s["features_dc"], s["scaling"], s["rotation"], s["opacity"])
+        rd = gb.GaussianRenderer()
+        res = mv.multiview_step(m, rd if fused else _NoSink(rd), cams, st, loss_fn, reduce=False)
+        return res["buffer"]
+
+    class _NoSink:
+        """The same renderer without the sink entry point."""
+        def __init__(self, rd):
+            self._rd = rd
+
+        def render(self, *a):
+            return self._rd.render(*a)
+
+    a, b = run(True), run(False)
+    assert float(b.flat.abs().max()) > 0
+    scale = float(b.flat[:b.param_elems].abs().max())
+    assert float((a.flat[:a.param_elems] - b.flat[:b.param_elems]).abs().max()) <= 2e-6 * scale
+    assert torch.allclose(a.grad_norm_sum, b.grad_norm_sum, rtol=1e-5, atol=1e-9 * scale)
+    assert torch.equal(a.vis_count, b.vis_count) and float(a.vis_count.max()) == 3.0
+    assert torch.equal(a.max_radii, b.max_radii) and float(a.max_radii.max()) > 0
