@@ -35,3 +35,9 @@ clean:
 	rm -rf $(BUILDDIR) $(LIBDIR)/libgsplat_b200.so oracle/_ref
 
 .PHONY: all oracle clean
+
+# kernel-variant experiments: make variant NAME=fwd24 DEFS="-DGS_FWD_MINB=24"  ->  build/variants/libgsplat_b200_fwd24.so
+variant:
+	@mkdir -p build/variants/$(NAME)
+	for f in abi project binsort raster; do $(NVCC) $(NVCCFLAGS) $(DEFS) -c $(CSRC)/$$f.cu -o build/variants/$(NAME)/$$f.o || exit 1; done
+	$(NVCC) -shared -o build/variants/libgsplat_b200_$(NAME).so build/variants/$(NAME)/*.o -cudart static

@@ -53,8 +53,12 @@ typedef enum GsStatus {
 #define GS_CAMERA_FLOATS 20
 
 /* Per-splat record consumed by the raster kernels: 12 floats = 3 x float4, 48-byte stride.
- *   {mx, my, c*Q00, c*(Q01+Q10)} {c*Q11, opacity, depth, r} {g, b, 0, 0},  c = -0.5*log2(e):
- * the splat weight exp(-0.5*s) of renderer.py:333-334 is then one exp2 of the quadratic form. */
+ *   {mx, my, c*Q00, c*(Q01+Q10)} {c*Q11, opacity, depth, r} {g, b, regular, 0},  c = -0.5*log2(e):
+ * the splat weight exp(-0.5*s) of renderer.py:333-334 is then one exp2 of the quadratic form.
+ * `regular` (1.0 / 0.0) marks splats with opacity in [0,1] and a positive-definite, well-conditioned
+ * conic, for which the two clamps of renderer.py:335,339 are identities: batches of such entries take
+ * a shorter instruction sequence in gs_raster_fwd / gs_raster_bwd (same results; a record with
+ * regular = 0 is always handled with the literal clamp sequence). */
 #define GS_SPLAT_REC_FLOATS 12
 
 int gs_abi_version(void);

@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
 ABI_VERSION = 7
 LIB_NAME = "libgsplat_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
+# GSPLAT_B200_LIB points at an alternative build of the same ABI (kernel-variant experiments, tools/)
+LIB_PATH = os.environ.get("GSPLAT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
 # symbol -> (restype, argtypes); mirrors include/gsplat_b200.h one to one
 _P = c_void_p

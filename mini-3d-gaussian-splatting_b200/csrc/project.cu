@@ -331,10 +331,18 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     depth_keys[i] = cnt > 0 ? __float_as_uint(p.Z) : (vis ? 0xFFFFFFFEu : 0xFFFFFFFFu);
     // raster record: conic pre-scaled by c = -0.5*log2(e) so that exp(-0.5*s) = exp2(quadratic form)
     const float kC = -0.72134752044448170f;
-    rec[i * 3 + 0] = make_float4(p.mx, p.my, kC * p.q00, kC * add_rn(p.q01, p.q10));
+    const float s00 = kC * p.q00, s01 = kC * add_rn(p.q01, p.q10), s11 = kC * p.q11;
+    rec[i * 3 + 0] = make_float4(p.mx, p.my, s00, s01);
     // depth kept finite in the record: masked-out pixels multiply it by 0 (0*inf would be NaN)
-    rec[i * 3 + 1] = make_float4(kC * p.q11, op, fminf(p.Z, 3.0e38f), cr);
-    rec[i * 3 + 2] = make_float4(cg, cb, 0.f, 0.f);
+    rec[i * 3 + 1] = make_float4(s11, op, fminf(p.Z, 3.0e38f), cr);
+    // "regular" flag for the compositing kernels' fast path: opacity in [0,1] and a positive-definite
+    // conic whose eigenvalue ratio is below 1e5 (det >= 1e-5 * trace^2), so that the quadratic form is
+    // <= 0 at every pixel up to its own rounding and both clamps of renderer.py:335,339 are identities.
+    // Every compare is false for NaN/inf inputs, which therefore take the general path.
+    const float det_s = s00 * s11 - 0.25f * s01 * s01, tr_s = s00 + s11;
+    const bool regular = (op >= 0.f) && (op <= 1.f) && (s00 < 0.f) && (s11 < 0.f) && (det_s >= 1e-5f * tr_s * tr_s) &&
+                         (tr_s > -1e30f);
+    rec[i * 3 + 2] = make_float4(cg, cb, regular ? 1.f : 0.f, 0.f);
 }
 
 // Backward (derived from the forward above).

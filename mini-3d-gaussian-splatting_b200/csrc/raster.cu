@@ -27,6 +27,19 @@
 
 namespace gs {
 
+#ifndef GS_FWD_MINB
+#define GS_FWD_MINB 1                  // min resident warps(=CTAs)/SM asked of ptxas for the forward kernel
+#endif
+#ifndef GS_BWD_MINB
+#define GS_BWD_MINB 16
+#endif
+#ifndef GS_CHAIN_PRED
+#define GS_CHAIN_PRED 1
+#endif
+#ifndef GS_BWD_GROUP
+#define GS_BWD_GROUP 2                 // list entries whose arithmetic runs between two warp barriers (backward)
+#endif
+
 constexpr int kPx = 8;                 // pixels per lane (1x8 strip) = 4 packed pairs
 constexpr int kPairs = kPx / 2;
 constexpr int kBatch = 32;             // list entries staged per round (one per lane)
@@ -64,31 +77,63 @@ struct EntryRow {
 };
 
 // renderer.py:330-346 for one pixel pair.  `A >= kTermA` encodes "this pixel has terminated (or
-// lies outside the image)", so no separate flag is carried.  Outputs: dx, e = exp(-s/2) (unclamped),
-// w = clamp(e), u = opacity*w (unclamped), contrib = (1-A)*clamp(u) ZEROED where the reference skips
-// the splat, and the two predicates.  Forward and backward both call this, so they agree bit for bit.
+// lies outside the image)", so no separate flag is carried.  Forward and backward both call this, so
+// they agree bit for bit.
+//
+// Two variants, chosen per batch of 32 list entries (warp-uniform):
+//  * kFast -- every entry of the batch carries the "regular" flag project_fwd stored in its record:
+//    opacity in [0,1] and a positive-definite, well-conditioned conic.  Then exp(-s/2) <= 1 (up to one
+//    rounding of s) and opacity*w <= 1, so both clamps of the reference are identities and are dropped,
+//    and the two skip rules (pixel terminated, w < 1e-5) are folded into the weight itself:
+//    wm = live ? e : 0 makes a, the contribution and every gradient term of that pixel an exact zero
+//    without further selects.
+//  * general -- the literal clamp / skip sequence, for anything else (opacities outside [0,1] through the
+//    covariance-mode inputs, degenerate conics).
 struct PairEval {
     float2 dx, e, w, u, a, T, contrib;
     bool act0, act1;
 };
 
+// wm = (A < kTermA && e >= kMinW) ? e : 0  -- two chained compares and one select
+__device__ __forceinline__ float live_weight(float A, float e) {
+    float wm;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\tsetp.ge.and.f32 p, %3, %4, p;\n\tselp.f32 %0, %3, 0f00000000, p;\n\t}"
+        : "=f"(wm) : "f"(A), "f"(kTermA), "f"(e), "f"(kMinW));
+    return wm;
+}
+__device__ __forceinline__ float live_select(float A, float w, float c) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\tsetp.ge.and.f32 p, %3, %4, p;\n\tselp.f32 %0, %5, 0f00000000, p;\n\t}"
+        : "=f"(r) : "f"(A), "f"(kTermA), "f"(w), "f"(kMinW), "f"(c));
+    return r;
+}
+
+template <bool kFast>
 __device__ __forceinline__ void eval_pair(float2 fpx, const EntryRow& r, float2 A, PairEval& ev) {
     ev.dx = add2(fpx, r.neg_mx);
     const float2 t = fma2(r.q00, ev.dx, r.qsdy);
     const float2 sp = fma2(ev.dx, t, r.q11dy2);          // -0.5*log2(e) * s
     ev.e = make_float2(ex2_approx(sp.x), ex2_approx(sp.y));
-    ev.w = make_float2(fminf(ev.e.x, 1.0f), fminf(ev.e.y, 1.0f));      // clamp(exp(.), 0, 1); exp >= 0
-    ev.u = mul2(bc2(r.op), ev.w);
-    ev.a = make_float2(__saturatef(ev.u.x), __saturatef(ev.u.y));      // clamp(opacity * w, 0, 1)
     ev.T = fma2(A, bc2(-1.0f), bc2(1.0f));                              // 1 - A, one rounding
-    const float2 c = mul2(ev.T, ev.a);
-    // a > 0 and contrib > 0 follow from opacity > kTinyOpacity, w >= 1e-5 and 1 - A >= 0.005;
-    // entries with opacity <= kTinyOpacity were staged with opacity 0 and contribute exact zeros
-    // (a = 0 => contrib = 0; the backward skips such an entry as a whole because its sum of
-    // contributions is zero)
-    ev.act0 = (A.x < kTermA) && (ev.w.x >= kMinW);
-    ev.act1 = (A.y < kTermA) && (ev.w.y >= kMinW);
-    ev.contrib = make_float2(ev.act0 ? c.x : 0.f, ev.act1 ? c.y : 0.f);
+    if (kFast) {
+        ev.w = make_float2(live_weight(A.x, ev.e.x), live_weight(A.y, ev.e.y));
+        ev.u = mul2(bc2(r.op), ev.w);
+        ev.a = ev.u;
+        ev.contrib = mul2(ev.T, ev.a);
+        ev.act0 = ev.w.x > 0.f;
+        ev.act1 = ev.w.y > 0.f;
+    } else {
+        ev.w = make_float2(fminf(ev.e.x, 1.0f), fminf(ev.e.y, 1.0f));      // clamp(exp(.), 0, 1); exp >= 0
+        ev.u = mul2(bc2(r.op), ev.w);
+        ev.a = make_float2(__saturatef(ev.u.x), __saturatef(ev.u.y));      // clamp(opacity * w, 0, 1)
+        const float2 c = mul2(ev.T, ev.a);
+        // a > 0 and contrib > 0 follow from opacity > kTinyOpacity, w >= 1e-5 and 1 - A >= 0.005;
+        // entries with opacity <= kTinyOpacity (or negative) were staged with opacity 0 and contribute
+        // exact zeros (a = 0 => contrib = 0; the backward skips such an entry as a whole)
+        ev.act0 = (A.x < kTermA) && (ev.w.x >= kMinW);
+        ev.act1 = (A.y < kTermA) && (ev.w.y >= kMinW);
+        ev.contrib = make_float2(live_select(A.x, ev.w.x, c.x), live_select(A.y, ev.w.y, c.y));
+    }
 }
 
 __device__ __forceinline__ void load_entry_row(const float4& r0, const float4& r1, float fpy, EntryRow& row, float& dy) {
@@ -100,8 +145,50 @@ __device__ __forceinline__ void load_entry_row(const float4& r0, const float4& r
     row.op = r1.y;
 }
 
+// Stages one list entry's record into shared memory; returns whether it is "regular" (fast path).
+__device__ __forceinline__ bool stage_entry(const float4* __restrict__ rec, int id, float4* dst) {
+    float4 q1 = __ldg(&rec[(int64_t)id * 3 + 1]);
+    const float4 q2 = __ldg(&rec[(int64_t)id * 3 + 2]);
+    q1.y = (q1.y > kTinyOpacity) ? q1.y : 0.f;      // opacity 0 => a = 0 => the entry adds exact zeros
+    dst[0] = __ldg(&rec[(int64_t)id * 3 + 0]);
+    dst[1] = q1;
+    dst[2] = q2;
+    return q2.z != 0.f;
+}
+
+// One batch of the forward walk (cnt staged entries).
+template <bool kFast, bool kTrack>
+__device__ __forceinline__ void fwd_batch(const float4* srec, int cnt, int first_index, float fpy, const float2 (&fpx)[kPairs],
+                                          float2 (&A)[kPairs], float2 (&Cr)[kPairs], float2 (&Cg)[kPairs],
+                                          float2 (&Cb)[kPairs], float2 (&Ds)[kPairs], int (&ncons)[kPx]) {
+#pragma unroll 2
+    for (int j = 0; j < cnt; ++j) {
+        const float4 r0 = srec[j * 3 + 0];          // mx, my, q00', qs'
+        const float4 r1 = srec[j * 3 + 1];          // q11', opacity (0 if tiny), z, r
+        const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);   // g, b
+        EntryRow row;
+        float dy;
+        load_entry_row(r0, r1, fpy, row, dy);
+        const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
+#pragma unroll
+        for (int p = 0; p < kPairs; ++p) {
+            PairEval ev;
+            eval_pair<kFast>(fpx[p], row, A[p], ev);
+            Cr[p] = fma2(ev.contrib, cr, Cr[p]);
+            Cg[p] = fma2(ev.contrib, cg, Cg[p]);
+            Cb[p] = fma2(ev.contrib, cb, Cb[p]);
+            Ds[p] = fma2(ev.contrib, z, Ds[p]);
+            A[p] = add2(A[p], ev.contrib);
+            if (kTrack) {                           // renderer.py:352: the entry that terminates the pixel
+                if (ev.act0 && A[p].x >= kTermA) ncons[2 * p] = first_index + j + 1;
+                if (ev.act1 && A[p].y >= kTermA) ncons[2 * p + 1] = first_index + j + 1;
+            }
+        }
+    }
+}
+
 template <bool kTrack>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, GS_FWD_MINB)
 raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, int any_visible,
@@ -140,40 +227,13 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         if (!__any_sync(0xffffffffu, alive)) break;
         const int cnt = min(kBatch, range.y - base);
         __syncwarp();                                   // previous batch fully read
-        if (lane < cnt) {
-            const int id = entry_ids[base + lane];
-            float4 q1 = __ldg(&rec[(int64_t)id * 3 + 1]);
-            q1.y = (q1.y > kTinyOpacity) ? q1.y : 0.f;      // opacity 0 => a = 0 => the entry adds exact zeros
-            srec[lane * 3 + 0] = __ldg(&rec[(int64_t)id * 3 + 0]);
-            srec[lane * 3 + 1] = q1;
-            srec[lane * 3 + 2] = __ldg(&rec[(int64_t)id * 3 + 2]);
-        }
+        bool regular = true;
+        if (lane < cnt) regular = stage_entry(rec, entry_ids[base + lane], &srec[lane * 3]);
+        const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
         walked = base - range.x + cnt;
-#pragma unroll 2
-        for (int j = 0; j < cnt; ++j) {
-            const float4 r0 = srec[j * 3 + 0];          // mx, my, q00', qs'
-            const float4 r1 = srec[j * 3 + 1];          // q11', opacity (0 if tiny), z, r
-            const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);   // g, b
-            EntryRow row;
-            float dy;
-            load_entry_row(r0, r1, fpy, row, dy);
-            const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
-#pragma unroll
-            for (int p = 0; p < kPairs; ++p) {
-                PairEval ev;
-                eval_pair(fpx[p], row, A[p], ev);
-                Cr[p] = fma2(ev.contrib, cr, Cr[p]);
-                Cg[p] = fma2(ev.contrib, cg, Cg[p]);
-                Cb[p] = fma2(ev.contrib, cb, Cb[p]);
-                Ds[p] = fma2(ev.contrib, z, Ds[p]);
-                A[p] = add2(A[p], ev.contrib);
-                if (kTrack) {                           // renderer.py:352: the entry that terminates the pixel
-                    if (ev.act0 && A[p].x >= kTermA) ncons[2 * p] = base - range.x + j + 1;
-                    if (ev.act1 && A[p].y >= kTermA) ncons[2 * p + 1] = base - range.x + j + 1;
-                }
-            }
-        }
+        if (all_regular) fwd_batch<true, kTrack>(srec, cnt, base - range.x, fpy, fpx, A, Cr, Cg, Cb, Ds, ncons);
+        else fwd_batch<false, kTrack>(srec, cnt, base - range.x, fpy, fpx, A, Cr, Cg, Cb, Ds, ncons);
     }
 
     // epilogue: renderer.py:359-367 (or :74-83 when nothing passed culling)
@@ -224,10 +284,156 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 // are accumulated; the five conic / mean sums follow once per entry:
 //   gQ00 = c*Sxx, gQ01 = gQ10 = c*dy*Sx, gQ11 = c*dy^2*Sh,
 //   g_mx = -(2 q00' Sx + qs' dy Sh),  g_my = -(2 q11' dy Sh + qs' Sx).
+constexpr int kBwdGroup = GS_BWD_GROUP;
+static_assert(32 % kBwdGroup == 0, "kBatch must be a multiple of the group");
 constexpr int kRedVals = 10;     // mx my | q00 q01 q11 | opacity | z | r g b
 constexpr int kRedStride = 36;   // floats per value row: 32 lanes + pad, keeps LDS.128 aligned
 
-__global__ void __launch_bounds__(32, 16)
+struct BwdOut {
+    float* base;              // lane v < 10: where reduced value v goes, base + id * stride
+    int stride;
+    float* red;               // [kRedVals][kRedStride] transpose buffer
+    const float4* red_src;    // this lane's slice of it
+    const int* sid;           // staged splat ids
+};
+
+// Second half of the per-entry reduction: lanes 0..29 each add a third of one value's 32 partials
+// (12 + 12 + 8, read as float4), lanes v < 10 collect the three thirds and send ONE vector atomic.
+// Lanes 30/31 and the third float4 of lanes >= 20 read in-bounds scratch that is never used.
+__device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id, int lane) {
+    const float4* src = out.red_src + buf * (kRedVals * kRedStride / 4);
+    const float4 q0 = src[0], q1 = src[1], q2 = src[2];
+    const float2 a01 = add2(make_float2(q0.x, q0.y), make_float2(q0.z, q0.w));
+    const float2 a23 = add2(make_float2(q1.x, q1.y), make_float2(q1.z, q1.w));
+    float2 a45 = add2(make_float2(q2.x, q2.y), make_float2(q2.z, q2.w));
+    a45.x = (lane < 20) ? a45.x : 0.f;                              // thirds 0 and 1 hold 12 partials
+    a45.y = (lane < 20) ? a45.y : 0.f;
+    const float2 acc = add2(add2(a01, a23), a45);
+    const float s = acc.x + acc.y;
+    const float s2 = __shfl_down_sync(0xffffffffu, s, 10);
+    const float s3 = __shfl_down_sync(0xffffffffu, s, 20);
+    if (lane < kRedVals) {
+        const float total = s + s2 + s3;
+        float* dst = out.base + (int64_t)id * out.stride;
+#ifdef GS_EXP_NOATOM     // timing experiment only (wrong results)
+        if (total == 123.456f) *dst = total;
+#else
+        atomicAdd(dst, total);
+        if (lane == 3) atomicAdd(dst + 1, total);      // Q01 and Q10 enter s symmetrically
+#endif
+    }
+}
+
+// Arithmetic of ONE list entry for this lane's 8 pixels; leaves the 10 per-lane partial sums in
+// rb[v * kRedStride + lane] (first half of the transpose reduction).  No barrier inside.
+template <bool kFast>
+__device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float fpy, const float2 (&fpx)[kPairs],
+                                          float2 (&A)[kPairs], float2 (&R)[kPairs], const float2 (&gCr)[kPairs],
+                                          const float2 (&gCg)[kPairs], const float2 (&gCb)[kPairs],
+                                          const float2 (&gDs)[kPairs], const float2 (&gA)[kPairs], float* rb) {
+    const float4 r0 = srec_j[0];
+    const float4 r1 = srec_j[1];
+    const float2 r2 = *reinterpret_cast<const float2*>(&srec_j[2]);
+    const float op = r1.y;
+    EntryRow row;
+    float dy;
+    load_entry_row(r0, r1, fpy, row, dy);
+    const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
+    float2 s_h = bc2(0.f), s_x = bc2(0.f), s_xx = bc2(0.f), s_op = bc2(0.f), s_z = bc2(0.f);
+    float2 s_cr = bc2(0.f), s_cg = bc2(0.f), s_cb = bc2(0.f);
+#pragma unroll
+    for (int p = 0; p < kPairs; ++p) {
+        PairEval ev;
+        eval_pair<kFast>(fpx[p], row, A[p], ev);
+        const float2 v = fma2(gCr[p], cr, fma2(gCg[p], cg, fma2(gCb[p], cb, fma2(gDs[p], z, gA[p]))));
+        R[p] = fma2(ev.contrib, v, R[p]);
+        A[p] = add2(A[p], ev.contrib);
+        // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
+        // a < 0.995, so 1 - a >= 0.005 and the approximate reciprocal is safe (a pixel that this
+        // entry terminates may see 1 - a ~ 0: its inf/NaN is discarded by the select).
+        const float2 oma = fma2(ev.a, bc2(-1.0f), bc2(1.0f));
+        float2 nsuf = mul2(R[p], make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
+        nsuf.x = (A[p].x >= kTermA) ? 0.f : nsuf.x;
+        nsuf.y = (A[p].y >= kTermA) ? 0.f : nsuf.y;
+        float2 g_a = fma2(ev.T, v, nsuf);
+        if (kFast) {
+            // ev.w is already zero where the reference skips the splat, and g_a only ever appears multiplied
+            // by it, so no further masking (both clamps are identities on this path).  dL/ds' = ln2*op*(w*g_a):
+            // the constant factor is applied once per entry, which also makes sum(h) the opacity sum itself.
+            const float2 gw = mul2(g_a, ev.w);
+            const float2 gwdx = mul2(gw, ev.dx);
+            s_op = add2(s_op, gw);
+            s_x = add2(s_x, gwdx);
+            s_xx = fma2(gwdx, ev.dx, s_xx);
+        } else {
+            // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
+            g_a.x = (ev.act0 && ev.u.x <= 1.f) ? g_a.x : 0.f;
+            g_a.y = (ev.act1 && ev.u.y <= 1.f) ? g_a.y : 0.f;
+            float2 h = mul2(ev.w, g_a);
+            s_op = add2(s_op, h);
+            h.x = (ev.e.x <= 1.f) ? h.x : 0.f;
+            h.y = (ev.e.y <= 1.f) ? h.y : 0.f;
+            const float2 hdx = mul2(h, ev.dx);
+            s_h = add2(s_h, h);
+            s_x = add2(s_x, hdx);
+            s_xx = fma2(hdx, ev.dx, s_xx);
+        }
+        s_cr = fma2(ev.contrib, gCr[p], s_cr);
+        s_cg = fma2(ev.contrib, gCg[p], s_cg);
+        s_cb = fma2(ev.contrib, gCb[p], s_cb);
+        s_z = fma2(ev.contrib, gDs[p], s_z);
+    }
+    // an entry staged with opacity 0 (<= kTinyOpacity, or negative) is one the reference skips (a <= 0):
+    // every sum below is then an exact zero except the opacity one, which is forced to zero
+    const float Sop_all = s_op.x + s_op.y;
+    const float Sop = (op > 0.f) ? Sop_all : 0.f;
+    const float hs = kLn2 * op;                         // dL/ds' = ln2 * op * w * dL/da
+    const float Sh = hs * (kFast ? Sop_all : (s_h.x + s_h.y)), Sx = hs * (s_x.x + s_x.y), Sxx = hs * (s_xx.x + s_xx.y);
+    const float dySh = dy * Sh;
+#ifdef GS_EXP_NORED      // timing experiment only (wrong results): no cross-lane reduction
+    {
+        const float k = Sh + Sx + Sxx + dySh + Sop + (s_z.x + s_z.y) + (s_cr.x + s_cr.y) + (s_cg.x + s_cg.y) + (s_cb.x + s_cb.y);
+        if (k == 123.456f) rb[lane] = k;
+        return;
+    }
+#endif
+    rb[0 * kRedStride + lane] = -fmaf(2.f * r0.z, Sx, r0.w * dySh);             // g_mx
+    rb[1 * kRedStride + lane] = -fmaf(2.f * r1.x, dySh, r0.w * Sx);             // g_my
+    rb[2 * kRedStride + lane] = kNegHalfLog2e * Sxx;                            // g_Q00
+    rb[3 * kRedStride + lane] = kNegHalfLog2e * (dy * Sx);                      // g_Q01 = g_Q10
+    rb[4 * kRedStride + lane] = kNegHalfLog2e * (dy * dySh);                    // g_Q11
+    rb[5 * kRedStride + lane] = Sop;
+    rb[6 * kRedStride + lane] = s_z.x + s_z.y;
+    rb[7 * kRedStride + lane] = s_cr.x + s_cr.y;
+    rb[8 * kRedStride + lane] = s_cg.x + s_cg.y;
+    rb[9 * kRedStride + lane] = s_cb.x + s_cb.y;
+}
+
+// One batch of the backward walk.  `cnt` is a multiple of kBwdGroup (the stager pads with null entries).
+// The entries are taken kBwdGroup at a time: their arithmetic runs back to back with no barrier in
+// between -- so the scheduler overlaps one entry's shared-memory and MUFU latencies with the next
+// entry's independent work (measured: the barrier after every entry, not the atomics, was what bound
+// this kernel; profiles/r1_v5_raster.md) -- then one __syncwarp, then the second halves of their reductions.
+template <bool kFast>
+__device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane, float fpy, const float2 (&fpx)[kPairs],
+                                          float2 (&A)[kPairs], float2 (&R)[kPairs], const float2 (&gCr)[kPairs],
+                                          const float2 (&gCg)[kPairs], const float2 (&gCb)[kPairs],
+                                          const float2 (&gDs)[kPairs], const float2 (&gA)[kPairs], const BwdOut& out) {
+    for (int j = 0; j < cnt; j += kBwdGroup) {
+#pragma unroll
+        for (int g = 0; g < kBwdGroup; ++g)
+            bwd_entry<kFast>(srec + (j + g) * 3, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA,
+                             out.red + g * (kRedVals * kRedStride));
+#ifndef GS_EXP_NORED
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < kBwdGroup; ++g) reduce_finish(out, g, out.sid[j + g], lane);
+        __syncwarp();
+#endif
+    }
+}
+
+__global__ void __launch_bounds__(32, GS_BWD_MINB)
 raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, const float* __restrict__ alpha,
@@ -238,7 +444,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                   float* __restrict__ g_colors, float* __restrict__ g_opac) {
     __shared__ float4 srec[kBatch * 3];
     __shared__ int sid[kBatch];
-    __shared__ __align__(16) float red[kRedVals * kRedStride];
+    __shared__ __align__(16) float red[kBwdGroup * kRedVals * kRedStride + 16];
 
     const int tile = blockIdx.x;
     const int lane = threadIdx.x;
@@ -305,6 +511,13 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         gDs[p] = make_float2(gd_[0], gd_[1]); gA[p] = make_float2(ga_[0], ga_[1]);
     }
 
+    BwdOut out;
+    out.base = out_base;
+    out.stride = out_stride;
+    out.red = red;
+    out.red_src = red_src;
+    out.sid = sid;
+
     const int2 range = tile_ranges[tile];
     const int end = range.x + tile_consumed[tile];
     for (int base = range.x; base < end; base += kBatch) {
@@ -314,93 +527,24 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         if (!__any_sync(0xffffffffu, alive)) break;
         const int cnt = min(kBatch, end - base);
         __syncwarp();
+        const int cnt_pad = (cnt + kBwdGroup - 1) / kBwdGroup * kBwdGroup;
+        bool regular = true;
         if (lane < cnt) {
             const int id = entry_ids[base + lane];
             sid[lane] = id;
-            float4 q1 = __ldg(&rec[(int64_t)id * 3 + 1]);
-            q1.y = (q1.y > kTinyOpacity) ? q1.y : 0.f;
-            srec[lane * 3 + 0] = __ldg(&rec[(int64_t)id * 3 + 0]);
-            srec[lane * 3 + 1] = q1;
-            srec[lane * 3 + 2] = __ldg(&rec[(int64_t)id * 3 + 2]);
+            regular = stage_entry(rec, id, &srec[lane * 3]);
+        } else if (lane < cnt_pad) {
+            // null entry: far outside every tile (weight exp2(-1e12) = 0) and opacity 0, so all ten sums are
+            // exact zeros; they are added to the batch's first splat
+            sid[lane] = entry_ids[base];
+            srec[lane * 3 + 0] = make_float4(1.0e6f, 0.f, -1.f, 0.f);
+            srec[lane * 3 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            srec[lane * 3 + 2] = make_float4(0.f, 0.f, 1.f, 0.f);
         }
+        const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
-        for (int j = 0; j < cnt; ++j) {
-            const float4 r0 = srec[j * 3 + 0];
-            const float4 r1 = srec[j * 3 + 1];
-            const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);
-            const float op = r1.y;
-            EntryRow row;
-            float dy;
-            load_entry_row(r0, r1, fpy, row, dy);
-            const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
-            const float2 hscale = bc2(kLn2 * op);
-            float2 s_h = bc2(0.f), s_x = bc2(0.f), s_xx = bc2(0.f), s_op = bc2(0.f), s_z = bc2(0.f);
-            float2 s_cr = bc2(0.f), s_cg = bc2(0.f), s_cb = bc2(0.f);
-#pragma unroll
-            for (int p = 0; p < kPairs; ++p) {
-                PairEval ev;
-                eval_pair(fpx[p], row, A[p], ev);
-                const float2 v = fma2(gCr[p], cr, fma2(gCg[p], cg, fma2(gCb[p], cb, fma2(gDs[p], z, gA[p]))));
-                R[p] = fma2(ev.contrib, v, R[p]);
-                A[p] = add2(A[p], ev.contrib);
-                // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
-                // a < 0.995, so 1 - a >= 0.005 and the approximate reciprocal is safe.
-                const float2 oma = fma2(ev.a, bc2(-1.0f), bc2(1.0f));
-                float2 nsuf = mul2(R[p], make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
-                nsuf.x = (A[p].x >= kTermA) ? 0.f : nsuf.x;
-                nsuf.y = (A[p].y >= kTermA) ? 0.f : nsuf.y;
-                float2 g_a = fma2(ev.T, v, nsuf);
-                // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
-                g_a.x = (ev.act0 && ev.u.x <= 1.f) ? g_a.x : 0.f;
-                g_a.y = (ev.act1 && ev.u.y <= 1.f) ? g_a.y : 0.f;
-                s_op = fma2(g_a, ev.w, s_op);
-                float2 h = mul2(mul2(ev.w, g_a), hscale);                      // dL/ds'
-                h.x = (ev.e.x <= 1.f) ? h.x : 0.f;
-                h.y = (ev.e.y <= 1.f) ? h.y : 0.f;
-                const float2 hdx = mul2(h, ev.dx);
-                s_h = add2(s_h, h);
-                s_x = add2(s_x, hdx);
-                s_xx = fma2(hdx, ev.dx, s_xx);
-                s_cr = fma2(ev.contrib, gCr[p], s_cr);
-                s_cg = fma2(ev.contrib, gCg[p], s_cg);
-                s_cb = fma2(ev.contrib, gCb[p], s_cb);
-                s_z = fma2(ev.contrib, gDs[p], s_z);
-            }
-            if (!(op > 0.f)) continue;      // staged as 0 when <= kTinyOpacity: the reference skips a <= 0 (warp-uniform)
-            const float Sh = s_h.x + s_h.y, Sx = s_x.x + s_x.y, Sxx = s_xx.x + s_xx.y;
-            const float dySh = dy * Sh;
-            // transpose-reduce the 10 sums over the warp: red[v][lane]
-            red[0 * kRedStride + lane] = -fmaf(2.f * r0.z, Sx, r0.w * dySh);             // g_mx
-            red[1 * kRedStride + lane] = -fmaf(2.f * r1.x, dySh, r0.w * Sx);             // g_my
-            red[2 * kRedStride + lane] = kNegHalfLog2e * Sxx;                            // g_Q00
-            red[3 * kRedStride + lane] = kNegHalfLog2e * (dy * Sx);                      // g_Q01 = g_Q10
-            red[4 * kRedStride + lane] = kNegHalfLog2e * (dy * dySh);                    // g_Q11
-            red[5 * kRedStride + lane] = s_op.x + s_op.y;
-            red[6 * kRedStride + lane] = s_z.x + s_z.y;
-            red[7 * kRedStride + lane] = s_cr.x + s_cr.y;
-            red[8 * kRedStride + lane] = s_cg.x + s_cg.y;
-            red[9 * kRedStride + lane] = s_cb.x + s_cb.y;
-            __syncwarp();
-            float s = 0.f;
-            if (lane < 30) {
-                const float4 q0 = red_src[0], q1 = red_src[1];
-                s = (q0.x + q0.y) + (q0.z + q0.w) + (q1.x + q1.y) + (q1.z + q1.w);
-                if (red_g < 2) {
-                    const float4 q2 = red_src[2];
-                    s += (q2.x + q2.y) + (q2.z + q2.w);
-                }
-            }
-            __syncwarp();
-            // lane v < 10 collects the three thirds of value v (lanes v, v+10, v+20)
-            const float s2 = __shfl_down_sync(0xffffffffu, s, 10);
-            const float s3 = __shfl_down_sync(0xffffffffu, s, 20);
-            if (lane < kRedVals) {
-                const float total = s + s2 + s3;
-                float* dst = out_base + (int64_t)sid[j] * out_stride;
-                atomicAdd(dst, total);
-                if (lane == 3) atomicAdd(dst + 1, total);      // Q01 and Q10 enter s symmetrically
-            }
-        }
+        if (all_regular) bwd_batch<true>(srec, cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
+        else bwd_batch<false>(srec, cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
     }
 }
 
