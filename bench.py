@@ -72,6 +72,11 @@ class ClockSampler:
                                        "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+            return
+        t0 = time.perf_counter()                 # nvidia-smi needs a moment to attach: wait for its first row
+        while time.perf_counter() - t0 < 5.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
+        self.skip = len(open(self.f.name).read().strip().splitlines())   # rows sampled before the timed region
 
     def stop(self):
         if self.p is None:
@@ -82,7 +87,10 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        lines = open(self.f.name).read().strip().splitlines()
+        rows = [r.split(",") for r in lines[getattr(self, "skip", 0):] if r.count(",") >= 8]
+        if not rows:
+            rows = [r.split(",") for r in lines if r.count(",") >= 8]
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}

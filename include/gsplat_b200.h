@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 7
+#define GS_ABI_VERSION 8
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -159,6 +159,12 @@ int gs_project_bwd(int64_t n,
  *                   tile counters walked in depth order, column scan, parallel scatter);
  *                   GS_BIN_RADIX: duplication + library (CUB) radix sort on the tile id + range
  *                   extraction -- kept for tile grids too large for the counters and as a cross-check.
+ * counters_dev (optional, counting sort only): the device address of gs_bin_prepare's counters.  When given,
+ *          `num_sorted` and `d` are CAPACITIES (pass n and the size of entry_ids): every kernel reads the
+ *          actual sizes on the device, and if D does not fit the capacity nothing is written and
+ *          tile_ranges stays zero -- the caller compares the counters with its capacity once they have
+ *          arrived on the host and, on overflow, repeats the call with exact sizes.  This lets the whole
+ *          forward be enqueued without waiting for the read-back (no bubble on the GPU).
  * Outputs: entry_ids [D] int32 splat ids grouped by tile, front to back;
  *          tile_ranges [num_tiles,2] int32 = [begin,end) into entry_ids;
  *          entry_keys [D] uint64 (optional, may be NULL) = tile_id<<32 | depth_bits of each entry,
@@ -182,6 +188,7 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
                 int32_t tiles_x, int32_t num_tiles, int32_t algo,
                 void* workspace, int64_t workspace_bytes,
                 int32_t* entry_ids, int32_t* tile_ranges, uint64_t* entry_keys,
+                const int64_t* counters_dev,
                 void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -189,7 +196,8 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
  *
  * bg: 3 floats (device).  `any_visible_host` (= counters[2] > 0) says whether any splat passed
  * culling: the reference returns the background ONCE, unclamped, when nothing is visible
- * (renderer.py:74-83) and adds it TWICE otherwise (renderer.py:273 + :359).
+ * (renderer.py:74-83) and adds it TWICE otherwise (renderer.py:273 + :359); if counters_dev is not NULL
+ * the kernel reads that fact from counters_dev[2] itself and any_visible_host is ignored.
  * Outputs: image [3,H,W], alpha [1,H,W], depth [1,H,W];
  *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue;
  *   tile_consumed [num_tiles] int32 = list entries the tile loaded before all its pixels saturated
@@ -200,6 +208,7 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
 int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
                   const float* splat_rec, const float* bg, int32_t any_visible_host,
+                  const int64_t* counters_dev,
                   float* image, float* alpha, float* depth,
                   float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
                   void* stream);

@@ -137,6 +137,24 @@ entry_keys_kernel(int64_t d, const uint32_t* __restrict__ sorted_tile_keys, cons
 constexpr int kChunk = 255;            // depth ranks per chunk: running counts fit uint8
 constexpr int kSuper = 256;            // chunks per super-chunk: 65 280 ranks, prefix fits uint16
 constexpr int kRowAlign = 128;         // table rows padded to 128 tiles (uchar4 / ushort4 / uint4 accesses)
+
+// Sizes of the frame.  Exact mode: the host read the counters back and passes them by value (dev = NULL).
+// Optimistic mode: the host passes CAPACITIES and the counters' device address; every kernel reads the
+// actual sizes itself and does nothing at all if the pairs would not fit (the caller then repeats the
+// stage in exact mode), so the launch does not wait for the read-back.
+struct BinSizes {
+    int64_t num_sorted;             // exact mode: value; optimistic: capacity (n)
+    int64_t d_capacity;
+    const int64_t* dev;             // counters {num_sorted, D, visible} or NULL
+};
+__device__ __forceinline__ bool resolve_sizes(const BinSizes& z, int64_t& num_sorted) {
+    num_sorted = z.num_sorted;
+    if (z.dev != nullptr) {
+        num_sorted = z.dev[0];
+        if (z.dev[1] > z.d_capacity) return false;
+    }
+    return true;
+}
 static_assert(kChunk <= 255 && (kSuper - 1) * kChunk <= 65535, "counter widths");
 
 // A splat's tile rectangle packed for warp broadcast: origin tile index, width, tile count, and the
@@ -172,7 +190,7 @@ __device__ __forceinline__ int tile_of(int k, int origin, int w, unsigned inv, i
 // shared-memory counters; lane k serves tiles k, k+32, ... of the current rectangle.  A splat's tiles
 // are distinct, so a splat never conflicts with itself; __syncwarp orders consecutive splats.
 __global__ void __launch_bounds__(32)
-chunk_walk_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
+chunk_walk_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
                   const ushort4* __restrict__ tile_rect, int tiles_x, int row_tiles,
                   uint8_t* __restrict__ local_pos, uint8_t* __restrict__ counts /* [chunks][row_tiles] */) {
     extern __shared__ uint32_t s_words[];
@@ -180,9 +198,12 @@ chunk_walk_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, co
     const int lane = threadIdx.x;
     const int64_t chunk = blockIdx.x;
     const int words = row_tiles >> 2;
+    int64_t num_sorted;
+    if (!resolve_sizes(sizes, num_sorted)) return;
+    const int64_t j_begin = chunk * kChunk;
+    if (j_begin >= num_sorted) return;                 // optimistic mode launches chunks for all n splats
     for (int w = lane; w < words; w += 32) s_words[w] = 0u;
     __syncwarp();
-    const int64_t j_begin = chunk * kChunk;
     const int64_t j_end = min(j_begin + (int64_t)kChunk, num_sorted);
     const ushort4 kNoRect = make_ushort4(1, 1, 0, 0);                  // width 0 -> count 0
     int id_cur = (j_begin + lane < j_end) ? sorted_ids[j_begin + lane] : -1;
@@ -235,10 +256,14 @@ chunk_walk_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, co
 // Block = 32 lanes (4 tiles each) x 32 segments of kSuper/32 chunks.
 constexpr int kSegChunks = kSuper / 32;
 __global__ void __launch_bounds__(1024)
-column_prefix_kernel(int num_chunks, int row_tiles, const uint8_t* __restrict__ counts, uint16_t* __restrict__ base16,
+column_prefix_kernel(BinSizes sizes, int row_tiles, const uint8_t* __restrict__ counts, uint16_t* __restrict__ base16,
                      uint32_t* __restrict__ super_tot /* [supers][row_tiles] */) {
     __shared__ uint4 s_seg[32][33];
     const int lane = threadIdx.x, seg = threadIdx.y;
+    int64_t num_sorted;
+    if (!resolve_sizes(sizes, num_sorted)) return;
+    const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
+    if ((int)blockIdx.y * kSuper >= num_chunks) return;
     const int t4 = (blockIdx.x * 32 + lane) * 4;
     const int sup = blockIdx.y;
     const int c0 = sup * kSuper + seg * kSegChunks;
@@ -270,9 +295,13 @@ column_prefix_kernel(int num_chunks, int row_tiles, const uint8_t* __restrict__ 
 // 3a. per tile: exclusive prefix over the super-chunks (in place) and the tile's total.  One thread per
 // tile, coalesced across the block; the loads of a column are independent and stay in flight together.
 __global__ void __launch_bounds__(128)
-super_prefix_kernel(int row_tiles, int num_supers, uint32_t* __restrict__ super_tab, uint32_t* __restrict__ tile_total) {
+super_prefix_kernel(BinSizes sizes, int row_tiles, uint32_t* __restrict__ super_tab, uint32_t* __restrict__ tile_total) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= row_tiles) return;
+    int64_t num_sorted;
+    if (!resolve_sizes(sizes, num_sorted)) return;
+    const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
+    const int num_supers = (num_chunks + kSuper - 1) / kSuper;
     uint32_t run = 0u;
     int s = 0;
     for (; s + 8 <= num_supers; s += 8) {
@@ -295,11 +324,13 @@ super_prefix_kernel(int row_tiles, int num_supers, uint32_t* __restrict__ super_
 
 // 3b. exclusive scan over tiles -> tile_start and tile_ranges [begin,end).  One block of 1024 threads.
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int num_tiles, const uint32_t* __restrict__ tile_total, uint32_t* __restrict__ tile_start,
+tile_scan_kernel(BinSizes sizes, int num_tiles, const uint32_t* __restrict__ tile_total, uint32_t* __restrict__ tile_start,
                  int32_t* __restrict__ ranges) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int64_t num_sorted_unused;
+    if (!resolve_sizes(sizes, num_sorted_unused)) return;
     if (tid == 0) s_carry = 0u;
     __syncthreads();
     for (int base = 0; base < num_tiles; base += 1024) {
@@ -342,7 +373,7 @@ tile_scan_kernel(int num_tiles, const uint32_t* __restrict__ tile_total, uint32_
 // at ~110 G store sectors/s whatever the load side does (batching the loads 4 ranks deep, 2x the
 // instructions in flight, changed nothing -- profiles/r1_v5_binning.md).
 __global__ void __launch_bounds__(256)
-scatter_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
+scatter_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
                const ushort4* __restrict__ tile_rect, int tiles_x, int row_tiles,
                const uint8_t* __restrict__ local_pos, const uint16_t* __restrict__ base16,
                const uint32_t* __restrict__ super_base, const uint32_t* __restrict__ tile_start,
@@ -350,6 +381,8 @@ scatter_kernel(int64_t num_sorted, const int32_t* __restrict__ sorted_ids, const
                uint64_t* __restrict__ entry_keys) {
     const int lane = threadIdx.x & 31;
     const int64_t j0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    int64_t num_sorted;
+    if (!resolve_sizes(sizes, num_sorted)) return;
     if (j0 >= num_sorted) return;
     const int64_t j = j0 + lane;
     int id = 0, cnt = 0;
@@ -519,7 +552,7 @@ extern "C" int gs_bin_prepare(int64_t n, const uint32_t* depth_keys, const int32
 extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32_t* sorted_ids, const int64_t* offsets,
                            const uint16_t* tile_rect, const uint32_t* depth_keys, int32_t tiles_x, int32_t num_tiles,
                            int32_t algo, void* workspace, int64_t workspace_bytes, int32_t* entry_ids,
-                           int32_t* tile_ranges, uint64_t* entry_keys, void* stream) {
+                           int32_t* tile_ranges, uint64_t* entry_keys, const int64_t* counters_dev, void* stream) {
     GS_REQUIRE(n >= 0 && num_sorted >= 0 && num_sorted <= n && d >= 0, "bad sizes");
     GS_REQUIRE(num_tiles > 0 && tiles_x > 0, "bad tile grid");
     GS_REQUIRE(tile_ranges != nullptr, "tile_ranges is NULL");
@@ -527,11 +560,13 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(tile_ranges);
     GS_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st));
-    if (d == 0 || num_sorted == 0) return GS_OK;
+    if (counters_dev == nullptr && (d == 0 || num_sorted == 0)) return GS_OK;
+    if (counters_dev != nullptr && (d == 0 || n == 0)) return GS_OK;      // no capacity: nothing can be written
     GS_REQUIRE(sorted_ids && offsets && tile_rect && workspace && entry_ids, "NULL array argument");
     GS_REQUIRE(entry_keys == nullptr || depth_keys != nullptr, "entry_keys needs depth_keys");
     GS_REQUIRE(algo >= 0 && algo <= 2, "algo must be 0 (auto), 1 (counting) or 2 (radix)");
     const bool counting = algo == GS_BIN_COUNTING || (algo == GS_BIN_AUTO && num_tiles <= kMaxCountingTiles);
+    GS_REQUIRE(counters_dev == nullptr || counting, "device-side sizes (counters_dev) need the counting sort");
     if (counting) {
         if (num_tiles > kMaxCountingTiles) {
             set_error("gs_bin_sort: the counting sort supports at most %d tiles (got %d); use algo 0 or 2", kMaxCountingTiles, num_tiles);
@@ -550,23 +585,24 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
         uint32_t* tile_start = (uint32_t*)(wsc + C.tile_start);
         uint8_t* local_pos = (uint8_t*)(wsc + C.local_pos);
         const size_t smem_walk = (size_t)C.row_tiles;
+        const BinSizes sizes = {num_sorted, d, counters_dev};
         if (smem_walk > 48 * 1024) GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_walk));
         // one warp + row_tiles bytes per CTA: residency is bounded by shared memory, so ask for the largest carve-out
         GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        chunk_walk_kernel<<<C.num_chunks, 32, smem_walk, st>>>(num_sorted, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x,
+        chunk_walk_kernel<<<C.num_chunks, 32, smem_walk, st>>>(sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x,
                                                               C.row_tiles, local_pos, counts);
         GS_CUDA_TRY(cudaGetLastError());
         column_prefix_kernel<<<dim3(C.row_tiles / kRowAlign, C.num_supers), dim3(32, 32), 0, st>>>(
-            C.num_chunks, C.row_tiles, counts, base16, super_tab);
+            sizes, C.row_tiles, counts, base16, super_tab);
         GS_CUDA_TRY(cudaGetLastError());
-        super_prefix_kernel<<<C.row_tiles / 128, 128, 0, st>>>(C.row_tiles, C.num_supers, super_tab, tile_total);
+        super_prefix_kernel<<<C.row_tiles / 128, 128, 0, st>>>(sizes, C.row_tiles, super_tab, tile_total);
         GS_CUDA_TRY(cudaGetLastError());
-        tile_scan_kernel<<<1, 1024, 0, st>>>(num_tiles, tile_total, tile_start, tile_ranges);
+        tile_scan_kernel<<<1, 1024, 0, st>>>(sizes, num_tiles, tile_total, tile_start, tile_ranges);
         GS_CUDA_TRY(cudaGetLastError());
         {
             const int64_t warps = (num_sorted + 31) / 32;
             scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-                num_sorted, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, local_pos, base16,
+                sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, local_pos, base16,
                 super_tab, tile_start, depth_keys, entry_ids, entry_keys);
         }
         GS_CUDA_TRY(cudaGetLastError());

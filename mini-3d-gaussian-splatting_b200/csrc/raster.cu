@@ -191,7 +191,7 @@ template <bool kTrack>
 __global__ void __launch_bounds__(32, GS_FWD_MINB)
 raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
-                  const float* __restrict__ bg_ptr, int any_visible,
+                  const float* __restrict__ bg_ptr, int any_visible_host, const int64_t* __restrict__ counters_dev,
                   float* __restrict__ image, float* __restrict__ alpha, float* __restrict__ depth,
                   float4* __restrict__ pix_state, int32_t* __restrict__ n_consumed,
                   int32_t* __restrict__ tile_consumed) {
@@ -204,6 +204,7 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     const int px0 = tx * kTile + (lane & 1) * kPx;
     const float bg0 = bg_ptr[0], bg1 = bg_ptr[1], bg2 = bg_ptr[2];
     const float fpy = (float)py;
+    const bool any_visible = counters_dev ? (counters_dev[2] > 0) : (any_visible_host != 0);
 
     float2 fpx[kPairs], A[kPairs], Cr[kPairs], Cg[kPairs], Cb[kPairs], Ds[kPairs];
     int ncons[kPx];
@@ -566,8 +567,8 @@ static int check_raster_args(int32_t img_w, int32_t img_h, int32_t tile_size, co
 
 extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, const int32_t* entry_ids,
                              const int32_t* tile_ranges, const float* splat_rec, const float* bg,
-                             int32_t any_visible_host, float* image, float* alpha, float* depth, float* pix_state,
-                             int32_t* n_consumed, int32_t* tile_consumed, void* stream) {
+                             int32_t any_visible_host, const int64_t* counters_dev, float* image, float* alpha, float* depth,
+                             float* pix_state, int32_t* n_consumed, int32_t* tile_consumed, void* stream) {
     const int rc = check_raster_args(img_w, img_h, tile_size, "gs_raster_fwd");
     if (rc != GS_OK) return rc;
     GS_REQUIRE(tile_ranges && bg && image && alpha && depth && pix_state && tile_consumed, "NULL array argument");
@@ -577,11 +578,11 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     if (n_consumed) {
         raster_fwd_kernel<true><<<tiles_x * tiles_y, 32, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            image, alpha, depth, (float4*)pix_state, n_consumed, tile_consumed);
+            counters_dev, image, alpha, depth, (float4*)pix_state, n_consumed, tile_consumed);
     } else {
         raster_fwd_kernel<false><<<tiles_x * tiles_y, 32, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            image, alpha, depth, (float4*)pix_state, nullptr, tile_consumed);
+            counters_dev, image, alpha, depth, (float4*)pix_state, nullptr, tile_consumed);
     }
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);

@@ -134,6 +134,7 @@ class _ProjectFn(torch.autograd.Function):
                 ptr(means2d), ptr(depths), ptr(conics), ptr(radii), ptr(colors), ptr(opac), ptr(vis),
                 ptr(tiles_touched), ptr(tile_rect), ptr(depth_keys), ptr(rec), _stream(dev)), "gs_project_fwd")
         ctx.meta = meta
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None instead of freshly zeroed tensors
         ctx.save_for_backward(xyz, scaling, rotation, cov3d, opacity, feat_src, features_rest)
         if meta.sink is not None:
             ctx.stat_inputs = (radii, vis)        # plain (non-graph) outputs: read by the fused statistics
@@ -218,15 +219,25 @@ def _sh_args(meta, feat_src, features_rest):
 
 
 class _RasterizeFn(torch.autograd.Function):
-    """Stage R (gs_raster_fwd / gs_raster_bwd).  `means2d` is the tensor returned to the caller as
-    ``viewspace_points``; its ``.grad`` after ``retain_grad()`` is what this backward emits."""
+    """Stage B+R: tile binning (gs_bin_sort, non-differentiable) and compositing (gs_raster_fwd /
+    gs_raster_bwd).  `means2d` is the tensor returned to the caller as ``viewspace_points``; its
+    ``.grad`` after ``retain_grad()`` is what this backward emits.
+
+    The binning needs the frame's pair count D, which only the device knows.  With a capacity learnt
+    from earlier frames (`bins.d_cap`) everything is enqueued at once with device-side sizes and the
+    counters are read back afterwards (no bubble on the GPU); the first frame, and a frame whose D
+    outgrows the capacity, go through the exact path: read D, then enqueue."""
 
     @staticmethod
-    def forward(ctx, meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, any_visible, track):
+    def forward(ctx, meta, bins, means2d, conics, depths, colors, opac, rec, bg, track):
         lib = _lib.load()
         dev = means2d.device
         H, W = meta.H, meta.W
-        tiles = tile_ranges.shape[0]
+        T = meta.tile
+        n = means2d.shape[0]
+        tiles_x, tiles_y = (W + T - 1) // T, (H + T - 1) // T
+        tiles = tiles_x * tiles_y
+        stream = _stream(dev)
         image = torch.empty((3, H, W), dtype=_F32, device=dev)
         alpha = torch.empty((1, H, W), dtype=_F32, device=dev)
         depth = torch.empty((1, H, W), dtype=_F32, device=dev)
@@ -234,13 +245,40 @@ class _RasterizeFn(torch.autograd.Function):
         # per-pixel consumed-entry counts: debug / parity output only (RenderSettings.debug)
         n_consumed = torch.empty((H, W), dtype=_I32, device=dev) if track else None
         tile_consumed = torch.empty((tiles,), dtype=_I32, device=dev)
-        with _timed("raster_fwd", dev):
-            check(lib.gs_raster_fwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
-                                    int(any_visible), ptr(image), ptr(alpha), ptr(depth), ptr(pix_state),
-                                    ptr(n_consumed), ptr(tile_consumed), _stream(dev)), "gs_raster_fwd")
+        tile_ranges = torch.empty((tiles, 2), dtype=_I32, device=dev)
+
+        def enqueue(num_sorted, d_size, counters_dev):
+            entry_ids = torch.empty(max(d_size, 1), dtype=_I32, device=dev)
+            ws_bytes = int(lib.gs_bin_workspace_bytes(num_sorted, d_size, tiles))
+            ws = torch.empty(ws_bytes, dtype=_U8, device=dev)
+            with _timed("bin_sort", dev):
+                check(lib.gs_bin_sort(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
+                                      ptr(bins.depth_keys), tiles_x, tiles, int(bins.algo), ptr(ws), ws.numel(),
+                                      ptr(entry_ids), ptr(tile_ranges), None, counters_dev, stream), "gs_bin_sort")
+            with _timed("raster_fwd", dev):
+                check(lib.gs_raster_fwd(W, H, T, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
+                                        int(bins.num_vis > 0) if counters_dev is None else 0, counters_dev,
+                                        ptr(image), ptr(alpha), ptr(depth), ptr(pix_state),
+                                        ptr(n_consumed), ptr(tile_consumed), stream), "gs_raster_fwd")
+            return entry_ids
+
+        entry_ids = None
+        if bins.d_cap is not None and bins.algo != 2 and n > 0:
+            entry_ids = enqueue(n, bins.d_cap, ptr(bins.counters))
+            bins.read_counters()
+            if bins.D > bins.d_cap:
+                entry_ids = None                        # did not fit: nothing was written, repeat with exact sizes
+        else:
+            bins.read_counters()
+        if entry_ids is None:
+            entry_ids = enqueue(bins.num_sorted, bins.D, None)
+        entry_ids = entry_ids[:bins.D]
+        bins.entry_ids, bins.tile_ranges = entry_ids, tile_ranges
+
         ctx.meta = meta
-        ctx.any_visible = any_visible
-        ctx.n = means2d.shape[0]
+        ctx.set_materialize_grads(False)
+        ctx.any_visible = bins.num_vis > 0
+        ctx.n = n
         ctx.save_for_backward(rec, entry_ids, tile_ranges, bg, alpha, pix_state, tile_consumed)
         if n_consumed is None:
             n_consumed = torch.empty(0, dtype=_I32, device=dev)
@@ -275,7 +313,33 @@ class _RasterizeFn(torch.autograd.Function):
                                         ptr(pix_state), ptr(tile_consumed), ptr(gi), ptr(ga), ptr(gd),
                                         ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                                         _stream(dev)), "gs_raster_bwd")
-        return None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None, None, None, None
+        return None, None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None
+
+
+class _FrameBins:
+    """Per-frame binning state handed to `_RasterizeFn`: the depth order, the device counters
+    {splats with tiles, tile pairs D, visible splats} and their asynchronous host copy."""
+
+    def __init__(self, renderer, device):
+        self.device = device
+        self.d_cap = renderer._d_cap.get(device.index) if renderer.optimistic_binning else None
+        slot = renderer._readback.get(device.index)
+        if slot is None:
+            slot = (torch.empty(3, dtype=_I64).pin_memory(), torch.cuda.Event())
+            renderer._readback[device.index] = slot
+        self._host, self._event = slot
+        self.num_sorted = self.D = self.num_vis = None
+        self.entry_ids = self.tile_ranges = None
+
+    def start_readback(self):
+        self._host.copy_(self.counters, non_blocking=True)
+        self._event.record(torch.cuda.current_stream(self.device))
+
+    def read_counters(self):
+        """The frame's one host wait: for the 24-byte counter copy, not for the kernels enqueued after it
+        (the reference syncs at the same point, on vis_mask.sum(), renderer.py:74)."""
+        self._event.synchronize()
+        self.num_sorted, self.D, self.num_vis = (int(v) for v in self._host.tolist())
 
 
 def _is_parameter_model(g) -> bool:
@@ -315,6 +379,12 @@ class GaussianRenderer:
         # Optional gradient sink (multiview.FlatGradBuffer): while set, the projection backward adds the
         # parameter gradients and the densification statistics straight into it (see `accumulate_into`).
         self.grad_sink = None
+        # Optimistic binning: enqueue tile binning + compositing with a pair capacity learnt from the
+        # previous frame instead of waiting for this frame's count (falls back to the exact path on
+        # the first frame and whenever the count outgrows the capacity).
+        self.optimistic_binning = True
+        self._d_cap: Dict[int, Optional[int]] = {}
+        self._readback: Dict[int, tuple] = {}
         _lib.load()   # fail at construction, not at first render, if the extension is missing
 
     def accumulate_into(self, sink):
@@ -414,35 +484,29 @@ class GaussianRenderer:
         (means2d, conics, depths, colors, opac, radii, vis, tiles_touched, tile_rect, depth_keys,
          rec) = _ProjectFn.apply(meta, xyz, scaling, rotation, cov3d, opacity, feat_src, rest)
 
-        # ---- stage S+B (non-differentiable) --------------------------------------------------
+        # ---- stage S (depth order, non-differentiable) ---------------------------------------------
         tiles_x, tiles_y = (W + T - 1) // T, (H + T - 1) // T
         num_tiles = tiles_x * tiles_y
         stream = _stream(device)
-        counters = torch.empty(3, dtype=_I64, device=device)
-        sorted_ids = torch.empty(n, dtype=_I32, device=device)
-        offsets = torch.empty(n, dtype=_I64, device=device)
+        bins = _FrameBins(self, device)
+        bins.tile_rect, bins.depth_keys, bins.algo = tile_rect, depth_keys, self.bin_algo
+        bins.counters = torch.empty(3, dtype=_I64, device=device)
+        bins.sorted_ids = torch.empty(n, dtype=_I32, device=device)
+        bins.offsets = torch.empty(n, dtype=_I64, device=device)
         ws_bytes = int(lib.gs_bin_workspace_bytes(n, 0, num_tiles))
         ws = torch.empty(ws_bytes, dtype=_U8, device=device)
         with _timed("bin_prepare", device):
-            check(lib.gs_bin_prepare(n, ptr(depth_keys), ptr(tiles_touched), ptr(ws), ws_bytes, ptr(sorted_ids),
-                                     ptr(offsets), ptr(counters), stream), "gs_bin_prepare")
-        # the one host sync of the frame (the reference syncs on vis_mask.sum() at renderer.py:74)
-        num_sorted, D, num_vis = (int(v) for v in counters.tolist())
-        tile_ranges = torch.empty((num_tiles, 2), dtype=_I32, device=device)
-        entry_ids = torch.empty(max(D, 1), dtype=_I32, device=device)
-        ws_bytes = int(lib.gs_bin_workspace_bytes(num_sorted, D, num_tiles))
-        if ws.numel() < ws_bytes:
-            ws = torch.empty(ws_bytes, dtype=_U8, device=device)
-        with _timed("bin_sort", device):
-            check(lib.gs_bin_sort(n, num_sorted, D, ptr(sorted_ids), ptr(offsets), ptr(tile_rect), ptr(depth_keys),
-                                  tiles_x, num_tiles, int(self.bin_algo), ptr(ws), ws.numel(), ptr(entry_ids),
-                                  ptr(tile_ranges), None, stream), "gs_bin_sort")
-        entry_ids = entry_ids[:D]
+            check(lib.gs_bin_prepare(n, ptr(depth_keys), ptr(tiles_touched), ptr(ws), ws_bytes, ptr(bins.sorted_ids),
+                                     ptr(bins.offsets), ptr(bins.counters), stream), "gs_bin_prepare")
+        bins.start_readback()
 
-        # ---- stage R -----------------------------------------------------------------------
+        # ---- stage B+R -----------------------------------------------------------------------
         image, alpha, depth, n_consumed, tile_consumed = _RasterizeFn.apply(
-            meta, means2d, conics, depths, colors, opac, rec, entry_ids, tile_ranges, bg, num_vis > 0,
-            bool(getattr(settings, "debug", False)))
+            meta, bins, means2d, conics, depths, colors, opac, rec, bg, bool(getattr(settings, "debug", False)))
+        num_sorted, D, num_vis = bins.num_sorted, bins.D, bins.num_vis
+        entry_ids, tile_ranges, sorted_ids = bins.entry_ids, bins.tile_ranges, bins.sorted_ids
+        # capacity for the next frame's optimistic binning: this frame's pair count plus a quarter
+        self._d_cap[device.index] = int(D * 1.25) + 4096 if self.optimistic_binning else None
 
         self.last_stats = {"num_visible": num_vis, "num_binned": num_sorted, "tile_pairs": D}
         self._last_debug = {"tile_consumed": tile_consumed, "n_consumed": n_consumed, "entry_ids": entry_ids,

@@ -273,7 +273,7 @@ def test_sort_keys_bit_exact_vs_oracle():
     for algo in (1, 2):          # hand-written counting sort, library radix sort: identical sequences
         entry_ids.fill_(-1); ekeys.fill_(-1)
         _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
-                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), st), "sort")
+                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, st), "sort")
         assert torch.equal(ekeys.cpu(), o["sort_keys"]), algo
         assert torch.equal(entry_ids.cpu().long(), o["sort_ids"]), algo
         util.assert_same_ranges(ranges, o["tile_ranges"])
@@ -574,3 +574,42 @@ def test_odd_splat_count_keeps_vector_accesses_aligned():
     util.assert_images_close(c_out, o_out, rd._last_debug["n_consumed"], o_out["n_consumed"], "odd n")
     for k in ("xyz", "scaling", "rotation", "opacity", "features_dc", "means2D"):
         assert util.rel_err(c_grads[k], o_grads[k]) < GRAD_TOL, k
+
+
+# ----------------------------------------------------------------------------------------------
+# (6) optimistic binning: device-side sizes with a capacity from the previous frame
+# ----------------------------------------------------------------------------------------------
+def test_optimistic_binning_equals_exact_path_and_survives_overflow():
+    import gsplat_b200 as gb
+    s = so.scene_aniso(6000, 91)
+    s["scaling"] = s["scaling"] + math.log(2.5)
+    m = util.cuda_model_from_params(s)
+    cams = [gb.Camera.orbit(k, 6, 208, 144) for k in (0, 1, 4)]
+    st = gb.RenderSettings(144, 208, torch.tensor([0.1, 0.2, 0.3]))
+
+    def frame(rd, cam):
+        for p in (m._xyz, m._scaling, m._rotation, m._opacity, m._features_dc, m._features_rest):
+            p.grad = None
+        out = rd.render(cam, m, st)
+        so.weighted_loss(out, tuple(t.cuda() for t in so.loss_weights(144, 208))).backward()
+        return ({k: out[k].detach().clone() for k in ("image", "alpha", "depth")}, rd._last_debug["entry_ids"].clone(),
+                rd._last_debug["tile_ranges"].clone(), m._xyz.grad.clone(), dict(rd.last_stats))
+
+    exact = gb.GaussianRenderer()
+    exact.optimistic_binning = False
+    opt = gb.GaussianRenderer()
+    assert opt.optimistic_binning
+    for i, cam in enumerate(cams):
+        a = frame(exact, cam)
+        if i == 2:
+            opt._d_cap[0] = 64                       # far too small: the frame must fall back to the exact path
+        b = frame(opt, cam)
+        assert a[4] == b[4]
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        for k in ("image", "alpha", "depth"):
+            assert torch.equal(a[0][k], b[0][k]), (i, k)
+        # atomics make the gradient sums order-dependent at rounding level
+        assert util.rel_err(b[3], a[3]) < 1e-5
+        if i >= 1:
+            assert opt._d_cap[0] >= b[4]["tile_pairs"]
+    assert exact._d_cap.get(0) is None
