@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "10"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
             return
@@ -333,8 +333,14 @@ def main():
             rd.render(cam, model, gb.RenderSettings(HEIGHT, WIDTH, torch.zeros(3, device=dev), debug=True))
         ncons = rd._last_debug["n_consumed"]
         evals = float(ncons.sum().item())      # pixel x list-entry evaluations actually walked
+    traffic, ncu_static = None, {}
+    try:                                         # DRAM bytes per launch from the committed ncu --set full capture
+        ncu_static = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top, {})
+        traffic = ncu_static["dram_read"] + ncu_static["dram_write"]
+    except Exception:
+        pass
     roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kernels[top]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[top]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "note": ("the compositing kernels are FP32/MUFU-issue bound, not HBM bound (SURVEY 8d): see `issue`"
                          if evals else "")}
     if evals:
@@ -342,7 +348,9 @@ def main():
         lane_roof = 148 * 128 * sm_clock * 1e6
         roofline["issue"] = {"pixel_splat_evals": evals, "evals_per_s": evals / (kernels[top]["ms"] * 1e-3),
                              "fp32_lane_instr_per_s_roof": lane_roof,
-                             "lane_instr_per_eval_at_roof": lane_roof / (evals / (kernels[top]["ms"] * 1e-3))}
+                             "lane_instr_per_eval_at_roof": lane_roof / (evals / (kernels[top]["ms"] * 1e-3)),
+                             "ncu_fma_pipe_active_pct": ncu_static.get("fma_pipe_active_pct"),
+                             "ncu_issue_active_pct": ncu_static.get("issue_active_pct")}
 
     if rank == 0:
         cpu = None
