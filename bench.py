@@ -144,7 +144,7 @@ def cpu_port_frames_per_s(sample_tiles: int, repeats: int = 1):
             "seconds_per_frame": frame}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,13 +166,21 @@ def run_reference_arm(args):
             "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     line["cpu_baseline"]["value"] = line["value"]
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
+    # the contract is ONE JSON line on stdout: anything a library prints there (NCCL prints its version on
+    # communicator creation) is sent to stderr instead, and the result line goes to the saved descriptor
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -183,7 +191,7 @@ def main():
     ap.add_argument("--splats", type=int, default=N_SPLATS, help="debug only; the reported metric is defined at 1M")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -308,6 +316,21 @@ def main():
         step_device()
     rmod.stage_timer.active = None
     per = {k: float(np.mean(v)) for k, v in timer.summary_ms().items()}
+    allreduce_ms = None
+    if world > 1:                                   # the exchange step alone: SUM of the flat buffer + MAX of the radii
+        ts = []
+        for _ in range(5):
+            mv.multiview_step(model, rd, [cam], settings, lambda out, vid: loss_fn(out, w_dev), buffer=buf, reduce=False)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            buf.all_reduce()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        t_ar = torch.tensor([float(np.mean(ts[1:]))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_ar, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(t_ar.item())
     st = rd.last_stats
     V, D = st["num_visible"], st["tile_pairs"]
     T = rd._last_debug["tile_ranges"].shape[0]
@@ -367,7 +390,9 @@ def main():
             "config": {"workload": WORKLOAD, "views_per_gpu_per_step": 1, "splats": n, "resolution": [WIDTH, HEIGHT],
                        "visible": V, "tile_pairs_D": D, "consumed_entries_E": E,
                        "l2": "flushed before every timed step (256 MiB memset); per-step working set > L2",
-                       "parallelism": f"view-sharded dp{world}, replicated Gaussians, NCCL allreduce of 16N floats" if world > 1 else "single GPU"},
+                       "parallelism": (f"view-sharded dp{world}, replicated Gaussians, gradient/statistics exchange of 17N floats: "
+                                       + ("one peer-memory kernel per rank over NVLink (gs_peer_allreduce)" if buf.peer is not None
+                                          else f"NCCL all_reduce (peer path unavailable: {buf.peer_error})")) if world > 1 else "single GPU"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -375,9 +400,13 @@ def main():
             "kernels": kernels,
             "wall_frames_per_s": world * args.steps / t_wall,
         }
+        if allreduce_ms is not None:
+            line["allreduce"] = {"ms": allreduce_ms, "bytes": int(buf.flat.numel() * 4 + buf.max_radii.numel() * 4),
+                                 "what": ("gs_peer_allreduce (SUM of the flat gradient/statistics buffer + MAX of the radii, one kernel)"
+                                          if buf.peer is not None else "NCCL all_reduce(SUM) of the flat buffer + all_reduce(MAX) of the radii")}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 8
+#define GS_ABI_VERSION 9
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -225,6 +225,22 @@ int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   float* g_means2d, float* g_conics, float* g_depths,
                   float* g_colors, float* g_opacities,
                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU exchange of the view-sharded step (no reference counterpart: the reference is single
+ * device).  Every rank holds the same flat fp32 buffer in peer-mapped (symmetric) memory;
+ * peer_ptrs_host[r] is rank r's buffer as seen from THIS process (HOST array of `world` device
+ * addresses).  One kernel: this rank reduces its 1/world slice of two regions across all peers --
+ * elementwise SUM over [sum_offset, sum_offset+sum_count) and MAX over [max_offset, max_offset+max_count)
+ * (floats, multiples of 4) -- and writes the result into every peer's buffer.  The caller must make sure
+ * (device-side barrier before) that all peers have finished producing their buffers and (barrier after)
+ * that all ranks' results have landed before anyone reads.  Results are bit-identical on all ranks.
+ * multicast_ptr: 0, or the NVSwitch multicast address of the same buffers; then the reduction runs inside
+ * the switch (multimem.ld_reduce / multimem.st) and the MAX region must hold non-negative floats.
+ * ------------------------------------------------------------------------------------- */
+int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int32_t world, int32_t rank,
+                      int64_t sum_offset, int64_t sum_count, int64_t max_offset, int64_t max_count,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ GPUs, gloo in the CPU tests (where a stand-in renderer supplies the per-view out
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -30,13 +31,21 @@ def shard_views(num_views: int, rank: int, world_size: int) -> List[int]:
 
 
 class FlatGradBuffer:
-    """One flat fp32 buffer whose slices are installed as the parameters' `.grad`."""
+    """One flat fp32 buffer whose slices are installed as the parameters' `.grad`.
 
-    def __init__(self, model):
+    `peer=True` (default when a CUDA process group with more than one rank is up; `GSPLAT_B200_PEER=0`
+    turns it off) places the buffer -- and the max-radii vector behind it -- in symmetric memory that
+    every rank of the node maps, and `all_reduce` then runs as ONE hand-written kernel per rank over NVLink
+    peer loads/stores (`gs_peer_allreduce`) between two device-side barriers, instead of two NCCL
+    collectives.  If symmetric memory cannot be set up the buffer falls back to NCCL and records why in
+    `peer_error`."""
+
+    def __init__(self, model, peer: Optional[bool] = None, group=None):
         self.model = model
         params = [getattr(model, name) for name in PARAM_ORDER]
         n = params[0].shape[0]
         sizes = [p.numel() for p in params]
+        device = params[0].device
         self.n = n
         # every segment starts on a 16-byte boundary (the kernels accumulate into them with float4 accesses)
         pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731
@@ -45,15 +54,52 @@ class FlatGradBuffer:
             offs.append(off)
             off = pad4(off + sz)
         self.param_elems = off
-        self.flat = torch.zeros(self.param_elems + 2 * pad4(n), dtype=torch.float32, device=params[0].device)
+        self.sum_elems = self.param_elems + 2 * pad4(n)
+        self.max_elems = pad4(n)
+        self.peer = None
+        self.peer_error = None
+        want_peer = peer if peer is not None else os.environ.get("GSPLAT_B200_PEER", "1") != "0"
+        storage = None
+        if (want_peer and device.type == "cuda" and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl"):
+            try:
+                storage = self._symmetric_storage(device, group)
+            except Exception as e:                      # NCCL remains available: not a silent CPU path
+                self.peer_error = f"{type(e).__name__}: {e}"
+                if peer:
+                    raise
+        if storage is None:
+            storage = torch.zeros(self.sum_elems + self.max_elems, dtype=torch.float32, device=device)
+        self.storage = storage
+        self.flat = storage[:self.sum_elems]
+        self.max_radii = storage[self.sum_elems:self.sum_elems + n]
         self.views = [self.flat[o:o + sz].view_as(p) for p, o, sz in zip(params, offs, sizes)]
         self.grad_norm_sum = self.flat[off:off + n]
         self.vis_count = self.flat[off + pad4(n):off + pad4(n) + n]
-        self.max_radii = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+
+    def _symmetric_storage(self, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(self.sum_elems + self.max_elems, dtype=torch.float32, device=device)
+        t.zero_()
+        handle = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        if len(ptrs) != dist.get_world_size(group) or any(p == 0 for p in ptrs):
+            raise RuntimeError(f"symmetric memory rendezvous returned {ptrs}")
+        import ctypes
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st) is implemented and correct but measured no faster
+        # than plain peer loads/stores on this platform (profiles/r1_v5_multigpu.md): opt-in
+        mc = 0
+        if os.environ.get("GSPLAT_B200_MULTICAST", "0") == "1":
+            try:
+                mc = int(handle.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+        self.peer = {"handle": handle, "rank": int(handle.rank), "world": int(handle.world_size),
+                     "ptrs": (ctypes.c_uint64 * len(ptrs))(*ptrs), "multicast": mc}
+        return t
 
     def install(self) -> None:
-        self.flat.zero_()
-        self.max_radii.zero_()
+        self.storage.zero_()
         for name, v in zip(PARAM_ORDER, self.views):
             getattr(self.model, name).grad = v
         rest = getattr(self.model, "_features_rest", None)
@@ -67,9 +113,21 @@ class FlatGradBuffer:
         torch.maximum(self.max_radii, radii * vis_f, out=self.max_radii)
 
     def all_reduce(self, group=None) -> None:
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        if self.peer is not None:
+            import ctypes
+            from . import _lib
+            h = self.peer["handle"]
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.storage.device).cuda_stream)
+            h.barrier(channel=0)                 # every rank's buffer is complete (device-side, on this stream)
+            _lib.check(_lib.load().gs_peer_allreduce(self.peer["ptrs"], self.peer["multicast"], self.peer["world"], self.peer["rank"],
+                                                     0, self.sum_elems, self.sum_elems, self.max_elems, stream),
+                       "gs_peer_allreduce")
+            h.barrier(channel=1)                 # every rank's slice has landed everywhere
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
 
 
 def multiview_step(model, renderer, cameras: Sequence, settings, loss_fn: Callable[[Dict[str, torch.Tensor], int], torch.Tensor],

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""torchrun tool: times the pieces of FlatGradBuffer.all_reduce's peer path (barriers alone, kernel alone)."""
+import json, os, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, torch.distributed as dist
+import gsplat_b200 as gb
+from importlib import import_module
+_lib = import_module("mini-3d-gaussian-splatting_b200._lib")
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+m = gb.GaussianModel(device=dev); m.create_from_random(1_000_000, 1.0, seed=0)
+buf = gb.multiview.FlatGradBuffer(m)
+h = buf.peer["handle"]; lib = _lib.load()
+st = lambda: ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+def kernel(mc):
+    _lib.check(lib.gs_peer_allreduce(buf.peer["ptrs"], mc, world, rank, 0, buf.sum_elems, buf.sum_elems, buf.max_elems, st()), "k")
+def timeit(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+out = {"world": world}
+out["two_barriers_ms"] = timeit(lambda: (h.barrier(channel=0), h.barrier(channel=1)))
+out["kernel_p2p_ms"] = timeit(lambda: kernel(0))
+if buf.peer["multicast"]:
+    out["kernel_multicast_ms"] = timeit(lambda: kernel(buf.peer["multicast"]))
+for mult in (1, 4, 8):
+    os.environ["GS_PEER_GRID_MULT"] = str(mult)
+    out[f"kernel_p2p_grid{mult}_ms"] = timeit(lambda: kernel(0))
+os.environ["GS_PEER_GRID_MULT"] = "2"
+out["lib"] = os.environ.get("GSPLAT_B200_LIB", "default")
+out["full_ms"] = timeit(buf.all_reduce)
+x = torch.empty(68_000_000 // 4, device=dev); y = torch.empty_like(x)
+out["local_copy_68MB_ms"] = timeit(lambda: y.copy_(x))
+if rank == 0: print(json.dumps(out), flush=True)
+dist.destroy_process_group()
