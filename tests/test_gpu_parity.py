@@ -613,3 +613,80 @@ def test_optimistic_binning_equals_exact_path_and_survives_overflow():
         if i >= 1:
             assert opt._d_cap[0] >= b[4]["tile_pairs"]
     assert exact._d_cap.get(0) is None
+
+
+# ----------------------------------------------------------------------------------------------
+# (7) inputs that leave the kernels' fast paths: opacities outside [0,1] and needle-thin covariances
+#     (general clamp/skip sequence of the compositing kernels), rectangles of more than 64 tiles
+#     (slow loops of the binning kernels)
+# ----------------------------------------------------------------------------------------------
+def _cov_mode_case(n, seed, W, H, scale_boost, thin_every, op_lo, op_hi, radius_max=50.0):
+    import gsplat_b200 as gb
+    s = so.scene_aniso(n, seed)
+    sc = s["scaling"] + math.log(scale_boost)
+    if thin_every < n:
+        sc[::thin_every, 2] = math.log(1e-4)               # needles: eigenvalue ratio of the conic far above 1e5
+        sc[::thin_every, 1] = math.log(1e-4)
+    g = torch.Generator().manual_seed(seed + 1)
+    op = op_lo + (op_hi - op_lo) * torch.rand(n, 1, generator=g)
+    op[3::17] = 0.0
+    cam = so.camera_orbit(1, 8, W, H)
+    bg = torch.tensor([0.05, 0.1, 0.15])
+    leaf = {"xyz": s["xyz"].clone().requires_grad_(True),
+            "cov": so.covariance_3d(sc, s["rotation"]).detach().requires_grad_(True),
+            "feat": s["features_dc"].clone().requires_grad_(True), "op": op.clone().requires_grad_(True)}
+    o = so.render(cam, leaf["xyz"], leaf["cov"], leaf["feat"].reshape(-1, 3), leaf["op"].reshape(-1), bg, H, W,
+                  radius_max=radius_max, return_stats=True)
+    so.weighted_loss(o, so.loss_weights(H, W)).backward()
+
+    class G:
+        pass
+    gg = G()
+    gg.get_xyz = leaf["xyz"].detach().cuda().requires_grad_(True)
+    gg.get_covariance = leaf["cov"].detach().cuda().requires_grad_(True)
+    gg.get_features = leaf["feat"].detach().cuda().requires_grad_(True)
+    gg.get_opacity = leaf["op"].detach().cuda().requires_grad_(True)
+    rd = gb.GaussianRenderer(radius_max=radius_max)
+    c = rd.render(util.cuda_camera(cam), gg, gb.RenderSettings(H, W, bg, debug=True))
+    so.weighted_loss(c, tuple(t.cuda() for t in so.loss_weights(H, W))).backward()
+    return o, leaf, c, gg, rd
+
+
+def test_general_path_opacity_outside_unit_interval():
+    """Opacities in [-0.2, 1.6] through the covariance-mode inputs: most batches hold a splat with opacity > 1,
+    so the compositing kernels run the literal clamp / skip sequence (clamp(opacity*w, 0, 1), a <= 0 skipped)."""
+    o, leaf, c, gg, rd = _cov_mode_case(1200, 301, 112, 80, 3.0, 10 ** 9, -0.2, 1.6)
+    util.assert_images_close(c, o, rd._last_debug["n_consumed"], o["n_consumed"], "general path")
+    assert torch.equal(c["visibility_filter"].cpu(), o["visibility_filter"])
+    assert torch.equal(rd._last_debug["entry_ids"].cpu().long(), o["sort_ids"])
+    assert util.rel_err(gg.get_xyz.grad, leaf["xyz"].grad) < GRAD_TOL
+    assert util.rel_err(gg.get_covariance.grad, leaf["cov"].grad) < GRAD_TOL
+    assert util.rel_err(gg.get_features.grad, leaf["feat"].grad) < GRAD_TOL
+    assert util.rel_err(gg.get_opacity.grad, leaf["op"].grad) < GRAD_TOL
+    # opacities <= 0 are skipped by the reference (renderer.py:340): no gradient reaches them
+    assert float(gg.get_opacity.grad[leaf["op"].detach().cuda() <= 0].abs().max()) == 0.0
+
+
+def test_needle_conics_take_the_general_path_and_stay_finite():
+    """Splats 1e-4 thin: the quadratic form of the reference is itself rounding noise there (terms of 1e6 cancel),
+    so parity is not defined; what must hold is that such records are not flagged regular, that the render is
+    finite, and that the well-conditioned splats' integer outputs are still exact."""
+    o, leaf, c, gg, rd = _cov_mode_case(600, 303, 96, 64, 3.0, 4, 0.05, 0.9)
+    for k in ("image", "alpha", "depth"):
+        assert bool(torch.isfinite(c[k]).all()), k
+    for t in (gg.get_xyz.grad, gg.get_covariance.grad, gg.get_features.grad, gg.get_opacity.grad):
+        assert bool(torch.isfinite(t).all())
+    assert torch.equal(c["visibility_filter"].cpu(), o["visibility_filter"])
+    assert torch.equal(rd._last_debug["entry_ids"].cpu().long(), o["sort_ids"])
+
+
+def test_rectangles_of_more_than_64_tiles():
+    """radius_max = 200 px: a splat's AABB can cover 26 x 26 tiles, the binning kernels' slow loops."""
+    o, leaf, c, gg, rd = _cov_mode_case(300, 302, 480, 320, 12.0, 1000, 0.05, 0.6, radius_max=200.0)
+    tt = rd._last_debug["tiles_touched"]
+    assert int(tt.max()) > 64
+    assert torch.equal(rd._last_debug["entry_ids"].cpu().long(), o["sort_ids"])
+    util.assert_same_ranges(rd._last_debug["tile_ranges"], o["tile_ranges"])
+    util.assert_images_close(c, o, rd._last_debug["n_consumed"], o["n_consumed"], "big rectangles")
+    assert util.rel_err(gg.get_xyz.grad, leaf["xyz"].grad) < GRAD_TOL
+    assert util.rel_err(gg.get_opacity.grad, leaf["op"].grad) < GRAD_TOL
