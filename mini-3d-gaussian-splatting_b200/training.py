@@ -77,7 +77,9 @@ class GaussianOptimizer:
         """Fresh Adam on the model's current parameters; state is discarded, as in the reference."""
         groups = [{"params": [getattr(self.model, attr)], "lr": getattr(self.config, lr), "name": name}
                   for name, attr, lr in self.GROUPS]
-        self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        # one fused multi-tensor kernel per step on CUDA parameters; plain Adam on CPU (tests)
+        fused = all(g["params"][0].is_cuda for g in groups)
+        self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15, fused=fused)
 
     def update_learning_rate(self, iteration: int) -> float:
         lr = self.xyz_scheduler.get_lr(iteration)
