@@ -158,7 +158,12 @@ int gs_project_bwd(int64_t n,
  *                   GS_BIN_AUTO): hand-written stable chunked counting sort (per-chunk shared-memory
  *                   tile counters walked in depth order, column scan, parallel scatter);
  *                   GS_BIN_RADIX: duplication + library (CUB) radix sort on the tile id + range
- *                   extraction -- kept for tile grids too large for the counters and as a cross-check.
+ *                   extraction -- kept for tile grids too large for the counters and as a cross-check;
+ *                   GS_BIN_BLOCKED: two-level counting sort -- ranks grouped by 8x8-tile block first (one
+ *                   radix pass on the block id), then each piece of a block's list is sorted by tile in
+ *                   shared memory and written out in coalesced runs.  Requires every tile rectangle to span
+ *                   at most 8 tiles per side (radius_max <= 50 px at 16-px tiles); the caller must choose
+ *                   another algorithm otherwise.
  * counters_dev (optional, counting sort only): the device address of gs_bin_prepare's counters.  When given,
  *          `num_sorted` and `d` are CAPACITIES (pass n and the size of entry_ids): every kernel reads the
  *          actual sizes on the device, and if D does not fit the capacity nothing is written and
@@ -173,6 +178,7 @@ int gs_project_bwd(int64_t n,
 #define GS_BIN_AUTO 0
 #define GS_BIN_COUNTING 1
 #define GS_BIN_RADIX 2
+#define GS_BIN_BLOCKED 3
 
 int64_t gs_bin_workspace_bytes(int64_t n, int64_t d_capacity, int32_t num_tiles);
 

@@ -476,6 +476,285 @@ static PrepareLayout prepare_layout(int64_t n) {
     return L;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Blocked (two-level) stable counting sort: GS_BIN_BLOCKED.
+//
+// The flat counting sort above ends in 26 M four-byte stores that each land in a different 32-byte sector
+// (~9.3 ps per pair, the floor of that design: profiles/r1_v5_binning.md).  Here the pairs are first grouped
+// coarsely, so that the final stores of one CTA are runs of neighbouring list entries:
+//   1. coarse_emit      every rank emits (block id, rank) for the <= 4 blocks of 8x8 tiles its rectangle meets
+//   2. CUB radix sort   ONE pass on the block id (<= 8 bits for up to 255 blocks), stable => rank order kept
+//   3. ranges / piece_map   per-block ranges of the coarse list, cut into pieces of kPiece ranks
+//   4. fine_count       per piece: pairs per local tile (shared-memory atomics)         pcount[piece][64]
+//   5. block_scan       per block: exclusive prefix over its pieces, tile totals        pbase[piece][64]
+//   6. tile_scan        tile_start / tile_ranges
+//   7. fine_write       per piece: cover bitsets per local tile (atomicOr), rank-ordered position of every pair
+//                       by popcount, pairs grouped by tile in shared memory, then copied out in runs:
+//                       entry_ids[tile_start + pbase + i] -- coalesced.
+// Requires every rectangle to span at most 8 tiles per side (true for radius_max <= 50 px at 16-px tiles: 101 px);
+// the caller (renderer.py) selects the flat sort otherwise.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlk = 8;
+constexpr int kBlkTiles = kBlk * kBlk;
+constexpr int kPiece = 128;               // ranks per fine CTA (4 warps)
+constexpr int kPieceWords = kPiece / 32;
+
+struct BlockGrid {
+    int tiles_x, tiles_y, blocks_x, num_blocks;
+};
+
+__global__ void __launch_bounds__(256)
+coarse_emit_kernel(BinSizes sizes, int64_t cap, const int32_t* __restrict__ sorted_ids, const ushort4* __restrict__ tile_rect,
+                   BlockGrid g, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cap) return;
+    int64_t num_sorted;
+    const bool ok = resolve_sizes(sizes, num_sorted);
+    uint32_t k[4] = {(uint32_t)g.num_blocks, (uint32_t)g.num_blocks, (uint32_t)g.num_blocks, (uint32_t)g.num_blocks};
+    if (ok && j < num_sorted) {
+        const ushort4 r = tile_rect[sorted_ids[j]];
+        const int bx0 = r.x / kBlk, bx1 = min((int)r.z / kBlk, bx0 + 1);
+        const int by0 = r.y / kBlk, by1 = min((int)r.w / kBlk, by0 + 1);
+        int q = 0;
+        for (int by = by0; by <= by1; ++by)
+            for (int bx = bx0; bx <= bx1; ++bx) k[q++] = (uint32_t)(by * g.blocks_x + bx);
+    }
+    reinterpret_cast<uint4*>(keys)[j] = make_uint4(k[0], k[1], k[2], k[3]);
+    reinterpret_cast<int4*>(vals)[j] = make_int4((int)j, (int)j, (int)j, (int)j);
+}
+
+// piece_begin[b] = number of pieces of the blocks before b; piece_begin[num_blocks] = all pieces.  One CTA.
+__global__ void __launch_bounds__(1024)
+piece_map_kernel(BinSizes sizes, int num_blocks, const int32_t* __restrict__ block_ranges, int32_t* __restrict__ piece_begin) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int64_t unused;
+    const bool ok = resolve_sizes(sizes, unused);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < num_blocks; base += 1024) {
+        const int b = base + tid;
+        int v = 0;
+        if (ok && b < num_blocks) v = (block_ranges[2 * b + 1] - block_ranges[2 * b] + kPiece - 1) / kPiece;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = s_warp[lane];
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += x;
+            }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const int begin = s_carry + s_warp[wid] + inc - v;
+        if (b < num_blocks) piece_begin[b] = begin;
+        __syncthreads();
+        if (tid == 1023) s_carry = begin + v;
+        __syncthreads();
+    }
+    if (tid == 0) piece_begin[num_blocks] = s_carry;
+}
+
+// Which piece is this CTA, which block does it belong to, which coarse entries does it cover.
+struct PieceInfo {
+    int block, bx, by, start, len;
+};
+__device__ __forceinline__ bool locate_piece(int p, const BlockGrid& g, const int32_t* __restrict__ piece_begin,
+                                             const int32_t* __restrict__ block_ranges, PieceInfo& info) {
+    if (p >= piece_begin[g.num_blocks]) return false;
+    int lo = 0, hi = g.num_blocks;                        // last b with piece_begin[b] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (piece_begin[mid] <= p) lo = mid; else hi = mid;
+    }
+    info.block = lo;
+    info.by = lo / g.blocks_x;
+    info.bx = lo - info.by * g.blocks_x;
+    const int kth = p - piece_begin[lo];
+    info.start = block_ranges[2 * lo] + kth * kPiece;
+    info.len = min(kPiece, block_ranges[2 * lo + 1] - info.start);
+    return true;
+}
+
+// the part of a rank's rectangle inside block (bx, by), in local tile coordinates (empty: lx0 > lx1)
+struct LocalRect {
+    int lx0, lx1, ly0, ly1, id;
+};
+__device__ __forceinline__ LocalRect local_rect(const PieceInfo& info, int i, const int32_t* __restrict__ coarse_ranks,
+                                                const int32_t* __restrict__ sorted_ids, const ushort4* __restrict__ tile_rect) {
+    LocalRect L = {1, 0, 1, 0, 0};
+    if (i < info.len) {
+        L.id = sorted_ids[coarse_ranks[info.start + i]];
+        const ushort4 r = tile_rect[L.id];
+        L.lx0 = max((int)r.x - info.bx * kBlk, 0);
+        L.lx1 = min((int)r.z - info.bx * kBlk, kBlk - 1);
+        L.ly0 = max((int)r.y - info.by * kBlk, 0);
+        L.ly1 = min((int)r.w - info.by * kBlk, kBlk - 1);
+    }
+    return L;
+}
+
+__global__ void __launch_bounds__(kPiece)
+fine_count_kernel(BinSizes sizes, BlockGrid g, const int32_t* __restrict__ piece_begin, const int32_t* __restrict__ block_ranges,
+                  const int32_t* __restrict__ coarse_ranks, const int32_t* __restrict__ sorted_ids,
+                  const ushort4* __restrict__ tile_rect, uint16_t* __restrict__ pcount /* [pieces][64] */) {
+    __shared__ int s_cnt[kBlkTiles];
+    int64_t unused;
+    if (!resolve_sizes(sizes, unused)) return;
+    PieceInfo info;
+    if (!locate_piece(blockIdx.x, g, piece_begin, block_ranges, info)) return;
+    if (threadIdx.x < kBlkTiles) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const LocalRect L = local_rect(info, threadIdx.x, coarse_ranks, sorted_ids, tile_rect);
+    for (int ly = L.ly0; ly <= L.ly1; ++ly)
+        for (int lx = L.lx0; lx <= L.lx1; ++lx) atomicAdd(&s_cnt[ly * kBlk + lx], 1);
+    __syncthreads();
+    if (threadIdx.x < kBlkTiles) pcount[(int64_t)blockIdx.x * kBlkTiles + threadIdx.x] = (uint16_t)s_cnt[threadIdx.x];
+}
+
+// per block: exclusive prefix over its pieces for each of its 64 tiles; the tiles' totals
+__global__ void __launch_bounds__(kBlkTiles)
+block_scan_kernel(BinSizes sizes, BlockGrid g, const int32_t* __restrict__ piece_begin, const uint16_t* __restrict__ pcount,
+                  uint32_t* __restrict__ pbase, uint32_t* __restrict__ tile_total) {
+    int64_t unused;
+    const bool ok = resolve_sizes(sizes, unused);
+    const int b = blockIdx.x, lt = threadIdx.x;
+    const int by = b / g.blocks_x, bx = b - by * g.blocks_x;
+    const int tx = bx * kBlk + (lt & (kBlk - 1)), ty = by * kBlk + (lt / kBlk);
+    uint32_t run = 0;
+    if (ok) {
+        const int p0 = piece_begin[b], p1 = piece_begin[b + 1];
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {
+            uint32_t c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = pcount[(int64_t)(p + q) * kBlkTiles + lt];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                pbase[(int64_t)(p + q) * kBlkTiles + lt] = run;
+                run += c[q];
+            }
+        }
+        for (; p < p1; ++p) {
+            const uint32_t c = pcount[(int64_t)p * kBlkTiles + lt];
+            pbase[(int64_t)p * kBlkTiles + lt] = run;
+            run += c;
+        }
+    }
+    if (tx < g.tiles_x && ty < g.tiles_y) tile_total[ty * g.tiles_x + tx] = run;
+}
+
+constexpr int kPieceMaxPairs = kPiece * kBlkTiles;      // 8192: every rank covers the whole block
+__global__ void __launch_bounds__(kPiece)
+fine_write_kernel(BinSizes sizes, BlockGrid g, const int32_t* __restrict__ piece_begin, const int32_t* __restrict__ block_ranges,
+                  const int32_t* __restrict__ coarse_ranks, const int32_t* __restrict__ sorted_ids,
+                  const ushort4* __restrict__ tile_rect, const uint32_t* __restrict__ pbase,
+                  const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ depth_keys,
+                  int32_t* __restrict__ entry_ids, uint64_t* __restrict__ entry_keys) {
+    __shared__ uint32_t s_cover[kBlkTiles][kPieceWords];      // which ranks of the piece cover local tile lt
+    __shared__ uint16_t s_wprefix[kBlkTiles][kPieceWords];    // covering ranks in the earlier warps
+    __shared__ uint32_t s_offset[kBlkTiles + 1];              // where tile lt's pairs start in s_out
+    __shared__ uint32_t s_gbase[kBlkTiles];                   // where they start in entry_ids
+    __shared__ int32_t s_out[kPieceMaxPairs];
+    __shared__ uint8_t s_tile[kPieceMaxPairs];
+    int64_t unused;
+    if (!resolve_sizes(sizes, unused)) return;
+    PieceInfo info;
+    if (!locate_piece(blockIdx.x, g, piece_begin, block_ranges, info)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int w = tid; w < kBlkTiles * kPieceWords; w += kPiece) (&s_cover[0][0])[w] = 0u;
+    __syncthreads();
+    const LocalRect L = local_rect(info, tid, coarse_ranks, sorted_ids, tile_rect);
+    for (int ly = L.ly0; ly <= L.ly1; ++ly)
+        for (int lx = L.lx0; lx <= L.lx1; ++lx) atomicOr(&s_cover[ly * kBlk + lx][warp], 1u << lane);
+    __syncthreads();
+    if (tid < kBlkTiles) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kPieceWords; ++w) {
+            s_wprefix[tid][w] = (uint16_t)run;
+            run += __popc(s_cover[tid][w]);
+        }
+        // exclusive scan of the 64 totals over two warps
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        s_offset[tid + 1] = inc;                                   // inclusive within the warp; fixed up below
+        const int tx = info.bx * kBlk + (tid & (kBlk - 1)), ty = info.by * kBlk + (tid / kBlk);
+        s_gbase[tid] = (tx < g.tiles_x && ty < g.tiles_y)
+                           ? tile_start[ty * g.tiles_x + tx] + pbase[(int64_t)blockIdx.x * kBlkTiles + tid] : 0u;
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < kBlkTiles) s_offset[tid + 1] += s_offset[32];   // second warp: add the first warp's total
+    if (tid == 0) s_offset[0] = 0u;
+    __syncthreads();
+    for (int ly = L.ly0; ly <= L.ly1; ++ly)
+        for (int lx = L.lx0; lx <= L.lx1; ++lx) {
+            const int lt = ly * kBlk + lx;
+            const uint32_t pos = s_offset[lt] + s_wprefix[lt][warp] + __popc(s_cover[lt][warp] & ((1u << lane) - 1u));
+            s_out[pos] = L.id;
+            s_tile[pos] = (uint8_t)lt;
+        }
+    __syncthreads();
+    const uint32_t total = s_offset[kBlkTiles];
+    for (uint32_t i = tid; i < total; i += kPiece) {
+        const int lt = s_tile[i];
+        const uint32_t pos = s_gbase[lt] + (i - s_offset[lt]);
+        const int id = s_out[i];
+        entry_ids[pos] = id;
+        if (entry_keys) {
+            const int tx = info.bx * kBlk + (lt & (kBlk - 1)), ty = info.by * kBlk + (lt / kBlk);
+            entry_keys[pos] = ((uint64_t)(uint32_t)(ty * g.tiles_x + tx) << 32) | (uint64_t)depth_keys[id];
+        }
+    }
+}
+
+struct BlockedLayout {
+    int64_t keys_in, keys_out, vals_in, vals_out, cub_temp, cub_bytes, block_ranges, piece_begin, pcount, pbase, tile_total,
+        tile_start, total;
+    int64_t items, max_pieces;
+    int bits;
+};
+static BlockedLayout blocked_layout(int64_t cap, int32_t num_tiles, int num_blocks_bound) {
+    BlockedLayout L;
+    L.items = 4 * (cap > 0 ? cap : 1);
+    L.bits = 1;
+    while ((1ll << L.bits) < (long long)num_blocks_bound + 1) ++L.bits;
+    L.max_pieces = (L.items + kPiece - 1) / kPiece + num_blocks_bound + 1;
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, L.items, 0, L.bits);
+    int64_t o = 0;
+    L.keys_in = o;      o += align_up(L.items * 4, 256);
+    L.keys_out = o;     o += align_up(L.items * 4, 256);
+    L.vals_in = o;      o += align_up(L.items * 4, 256);
+    L.vals_out = o;     o += align_up(L.items * 4, 256);
+    L.cub_temp = o;     L.cub_bytes = align_up((int64_t)sort_bytes, 256); o += L.cub_bytes;
+    L.block_ranges = o; o += align_up((int64_t)(num_blocks_bound + 1) * 8, 256);
+    L.piece_begin = o;  o += align_up((int64_t)(num_blocks_bound + 2) * 4, 256);
+    L.pcount = o;       o += align_up(L.max_pieces * kBlkTiles * 2, 256);
+    L.pbase = o;        o += align_up(L.max_pieces * kBlkTiles * 4, 256);
+    L.tile_total = o;   o += align_up((int64_t)num_tiles * 4, 256);
+    L.tile_start = o;   o += align_up((int64_t)num_tiles * 4, 256);
+    L.total = o;
+    return L;
+}
+// any tile grid of num_tiles tiles has at most this many 8x8 blocks (a 1 x num_tiles strip)
+static int blocks_bound(int32_t num_tiles) { return (num_tiles + kBlk - 1) / kBlk + 1; }
+
 struct SortLayout {
     int64_t keys_in, keys_out, vals_in, cub_temp, cub_bytes, total;
 };
@@ -504,8 +783,10 @@ extern "C" int64_t gs_bin_workspace_bytes(int64_t n, int64_t d_capacity, int32_t
     const int64_t a = prepare_layout(n > 0 ? n : 1).total;
     const int64_t b = sort_layout(d_capacity > 0 ? d_capacity : 1, num_tiles).total;
     const int64_t c = num_tiles <= kMaxCountingTiles ? count_layout(n > 0 ? n : 1, d_capacity > 0 ? d_capacity : 1, num_tiles).total : 0;
+    const int64_t e = blocked_layout(n > 0 ? n : 1, num_tiles, blocks_bound(num_tiles)).total;
     int64_t m = a > b ? a : b;
     if (c > m) m = c;
+    if (e > m) m = e;
     return m + 256;
 }
 
@@ -564,9 +845,62 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     if (counters_dev != nullptr && (d == 0 || n == 0)) return GS_OK;      // no capacity: nothing can be written
     GS_REQUIRE(sorted_ids && offsets && tile_rect && workspace && entry_ids, "NULL array argument");
     GS_REQUIRE(entry_keys == nullptr || depth_keys != nullptr, "entry_keys needs depth_keys");
-    GS_REQUIRE(algo >= 0 && algo <= 2, "algo must be 0 (auto), 1 (counting) or 2 (radix)");
+    GS_REQUIRE(algo >= 0 && algo <= 3, "algo must be 0 (auto), 1 (counting), 2 (radix) or 3 (blocked)");
     const bool counting = algo == GS_BIN_COUNTING || (algo == GS_BIN_AUTO && num_tiles <= kMaxCountingTiles);
-    GS_REQUIRE(counters_dev == nullptr || counting, "device-side sizes (counters_dev) need the counting sort");
+    GS_REQUIRE(counters_dev == nullptr || counting || algo == GS_BIN_BLOCKED, "device-side sizes (counters_dev) need a counting sort");
+    if (algo == GS_BIN_BLOCKED) {
+        GS_REQUIRE(num_tiles % tiles_x == 0, "num_tiles must be tiles_x * tiles_y");
+        BlockGrid g;
+        g.tiles_x = tiles_x;
+        g.tiles_y = num_tiles / tiles_x;
+        g.blocks_x = (g.tiles_x + kBlk - 1) / kBlk;
+        g.num_blocks = g.blocks_x * ((g.tiles_y + kBlk - 1) / kBlk);
+        const BlockedLayout L = blocked_layout(num_sorted, num_tiles, blocks_bound(num_tiles));
+        if (workspace_bytes < L.total) {
+            set_error("gs_bin_sort: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)L.total);
+            return GS_ERR_WORKSPACE_TOO_SMALL;
+        }
+        char* w = (char*)workspace;
+        uint32_t* keys_in = (uint32_t*)(w + L.keys_in);
+        uint32_t* keys_out = (uint32_t*)(w + L.keys_out);
+        int32_t* vals_in = (int32_t*)(w + L.vals_in);
+        int32_t* vals_out = (int32_t*)(w + L.vals_out);
+        int32_t* block_ranges = (int32_t*)(w + L.block_ranges);
+        int32_t* piece_begin = (int32_t*)(w + L.piece_begin);
+        uint16_t* pcount = (uint16_t*)(w + L.pcount);
+        uint32_t* pbase = (uint32_t*)(w + L.pbase);
+        uint32_t* tile_total = (uint32_t*)(w + L.tile_total);
+        uint32_t* tile_start = (uint32_t*)(w + L.tile_start);
+        const BinSizes sizes = {num_sorted, d, counters_dev};
+        const int64_t cap = num_sorted;
+        int bits = 1;
+        while ((1 << bits) < g.num_blocks + 1) ++bits;
+        coarse_emit_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(sizes, cap, sorted_ids, (const ushort4*)tile_rect, g,
+                                                                          keys_in, vals_in);
+        GS_CUDA_TRY(cudaGetLastError());
+        size_t cub_bytes = (size_t)L.cub_bytes;
+        GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w + L.cub_temp, cub_bytes, (const uint32_t*)keys_in, keys_out,
+                                                    (const int32_t*)vals_in, vals_out, 4 * cap, 0, bits, st));
+        GS_CUDA_TRY(cudaMemsetAsync(block_ranges, 0, (size_t)(g.num_blocks + 1) * 8, st));
+        ranges_kernel<<<(unsigned)((4 * cap + 255) / 256), 256, 0, st>>>(4 * cap, keys_out, block_ranges);
+        GS_CUDA_TRY(cudaGetLastError());
+        piece_map_kernel<<<1, 1024, 0, st>>>(sizes, g.num_blocks, block_ranges, piece_begin);
+        GS_CUDA_TRY(cudaGetLastError());
+        const unsigned max_pieces = (unsigned)((4 * cap + kPiece - 1) / kPiece + g.num_blocks);
+        fine_count_kernel<<<max_pieces, kPiece, 0, st>>>(sizes, g, piece_begin, block_ranges, vals_out, sorted_ids,
+                                                         (const ushort4*)tile_rect, pcount);
+        GS_CUDA_TRY(cudaGetLastError());
+        block_scan_kernel<<<g.num_blocks, kBlkTiles, 0, st>>>(sizes, g, piece_begin, pcount, pbase, tile_total);
+        GS_CUDA_TRY(cudaGetLastError());
+        tile_scan_kernel<<<1, 1024, 0, st>>>(sizes, num_tiles, tile_total, tile_start, tile_ranges);
+        GS_CUDA_TRY(cudaGetLastError());
+        fine_write_kernel<<<max_pieces, kPiece, 0, st>>>(sizes, g, piece_begin, block_ranges, vals_out, sorted_ids,
+                                                         (const ushort4*)tile_rect, pbase, tile_start, depth_keys, entry_ids,
+                                                         entry_keys);
+        GS_CUDA_TRY(cudaGetLastError());
+        count_launches(7);
+        return GS_OK;
+    }
     if (counting) {
         if (num_tiles > kMaxCountingTiles) {
             set_error("gs_bin_sort: the counting sort supports at most %d tiles (got %d); use algo 0 or 2", kMaxCountingTiles, num_tiles);

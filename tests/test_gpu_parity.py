@@ -270,7 +270,7 @@ def test_sort_keys_bit_exact_vs_oracle():
     entry_ids = torch.empty(D, dtype=torch.int32, device="cuda")
     ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device="cuda")
     ekeys = torch.empty(D, dtype=torch.int64, device="cuda")
-    for algo in (1, 2):          # hand-written counting sort, library radix sort: identical sequences
+    for algo in (1, 2, 3):       # flat counting sort, library radix sort, blocked counting sort: identical sequences
         entry_ids.fill_(-1); ekeys.fill_(-1)
         _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
                                    algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, st), "sort")

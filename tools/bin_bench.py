@@ -34,7 +34,7 @@ ranges = torch.empty((tiles, 2), dtype=torch.int32, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
 import ctypes
 ref = None
-for algo in (1, 2):
+for algo in (1, 2, 3):
     ts = []
     for r in range(reps + 2):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
