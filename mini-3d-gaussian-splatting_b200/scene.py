@@ -142,6 +142,25 @@ class GaussianModel(nn.Module):
                   torch.full((num_points, 1), -2.0, device=dev))
 
     @torch.no_grad()
+    def create_from_pcd(self, pcd_path: str, spatial_lr_scale: float = 1.0, seed: Optional[int] = None) -> None:
+        """Initialise from a point cloud file (gaussian_model.py:43-76): colours -> features_dc (white when the
+        file has none), log-scale = log(0.01 * max(extent, 0.01) * spatial_lr_scale), random unit quaternions,
+        opacity parameter 0.5."""
+        from .io_utils import IOUtils
+        points, colors = IOUtils.load_pcd(pcd_path)
+        if points.size == 0:
+            raise ValueError("No points found in the PCD file.")
+        n = points.shape[0]
+        dev = self._xyz.device
+        xyz = torch.from_numpy(points).float()
+        cols = torch.ones(n, 3) if colors is None else torch.from_numpy(colors).float()
+        extent = float((xyz.max(dim=0).values - xyz.min(dim=0).values).mean())
+        base_scale = 0.01 * max(extent, 1e-2) * spatial_lr_scale
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        rot = F.normalize(torch.randn(n, 4, generator=g), dim=-1)
+        self._set(xyz.to(dev), cols[:, None, :].contiguous().to(dev), torch.zeros(n, 15, 3, device=dev),
+                  torch.full((n, 3), math.log(base_scale), device=dev), rot.to(dev), torch.full((n, 1), 0.5, device=dev))
+
     def create_from_tensors(self, xyz, features_dc, scaling, rotation, opacity, features_rest=None) -> None:
         dev = self._xyz.device
         n = xyz.shape[0]
