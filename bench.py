@@ -233,26 +233,36 @@ def main():
         return res["losses"][0]
 
     cam_wv_host = cam.world_view_transform().clone().pin_memory()
-    stage = [torch.empty_like(t, device=dev) for t in w_host]
+    # two staging sets: step k computes from set k%2 while the copy stream already uploads step k+1's inputs
+    stage = [[torch.empty_like(t, device=dev) for t in w_host] for _ in range(2)]
+    uploaded = [torch.cuda.Event(), torch.cuda.Event()]
     copy_stream = torch.cuda.Stream(device=dev)
+    e2e_state = {"k": 0, "primed": False}
+
+    def upload(slot):
+        # a slot is free again once the step that read it has ended (every step ends with a host read of its loss)
+        with torch.cuda.stream(copy_stream):
+            for s_, h_ in zip(stage[slot], w_host):
+                s_.copy_(h_, non_blocking=True)
+            uploaded[slot].record(copy_stream)
 
     def step_e2e():
-        # this step's host inputs: camera pose + loss weights (the "ground truth" side of the step).  The
-        # 41.5 MB weight upload runs on a copy stream under projection / binning / compositing; the loss
-        # waits for it.  Every step ends with a host read of the loss, so the staging buffers are free again.
+        # this step's host inputs: camera pose + loss weights (the "ground truth" side of the step), 41.5 MB from
+        # pinned memory.  Every step's upload is inside the timed region; it is issued one step ahead (input
+        # double-buffering, as a data loader does), so it runs under the previous step's kernels.
+        k = e2e_state["k"]
+        if not e2e_state["primed"]:
+            upload(k % 2)
+            e2e_state["primed"] = True
         c = gb.Camera(WIDTH, HEIGHT, cam._FoVx, cam._FoVy, world_view=cam_wv_host)   # pose: 64 B, passed by value to the kernels
-        copy_stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(copy_stream):
-            for s_, h_ in zip(stage, w_host):
-                s_.copy_(h_, non_blocking=True)
-            uploaded = torch.cuda.Event()
-            uploaded.record(copy_stream)
+        upload((k + 1) % 2)                                      # next step's inputs
 
         def loss_after_upload(out, vid):
-            torch.cuda.current_stream(dev).wait_event(uploaded)
-            return loss_fn(out, stage)
+            torch.cuda.current_stream(dev).wait_event(uploaded[k % 2])
+            return loss_fn(out, stage[k % 2])
 
         res = mv.multiview_step(model, rd, [c], settings, loss_after_upload, buffer=buf, reduce=world > 1)
+        e2e_state["k"] = k + 1
         return float(res["losses"][0].item())                    # D2H read of the step's result
 
     def barrier():

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 9
+#define GS_ABI_VERSION 10
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -247,6 +247,32 @@ int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
 int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int32_t world, int32_t rank,
                       int64_t sum_offset, int64_t sum_count, int64_t max_offset, int64_t max_count,
                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Density control on the device: GaussianModel.density_and_split / density_and_clone / prune_points
+ * (src/core/gaussian_model.py:130-197) as driven by DensityController.densify_and_prune
+ * (src/core/optimizer.py:43-71), as one plan pass + one apply pass.
+ *   clone: |grad[i]| > grad_threshold and mean(exp(scaling_log[i])) < small_sigma -> keep + jittered copy
+ *          (xyz + noise[i] * 0.5*mean sigma);
+ *   split: |grad[i]| > grad_threshold and mean sigma > large_sigma -> replaced by two children at
+ *          xyz -+ R[:,0]*0.5*mean sigma, sigma*0.75, opacity logit clamped to [-6,6];
+ *   prune: rows with sigmoid(opacity) <= min_opacity are dropped.
+ * gs_densify_plan classifies and scans; counts (device, 4 x int64) = {surviving originals, clone copies,
+ * split parents, total rows}.  The caller reads the counts, allocates the six output arrays with `total`
+ * rows and calls gs_densify_apply with the same workspace.  Output order: surviving originals, clone
+ * copies, "minus" children, "plus" children -- each in index order (what the sequential formulation yields).
+ * ------------------------------------------------------------------------------------- */
+int64_t gs_densify_workspace_bytes(int64_t n);
+
+int gs_densify_plan(int64_t n, const float* scaling_log, const float* opacity, const float* grad,
+                    float grad_threshold, float small_sigma, float large_sigma, float min_opacity,
+                    void* workspace, int64_t workspace_bytes, int64_t* counts, void* stream);
+
+int gs_densify_apply(int64_t n, const void* workspace, int64_t kept, int64_t cloned, int64_t split,
+                     const float* xyz, const float* features_dc, const float* features_rest,
+                     const float* scaling_log, const float* rotation, const float* opacity, const float* noise,
+                     float* o_xyz, float* o_features_dc, float* o_features_rest, float* o_scaling_log,
+                     float* o_rotation, float* o_opacity, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,17 +53,21 @@ class _ViewMeta:
 def _camera_block(camera) -> ctypes.Array:
     """renderer.py:140-152: intrinsics in python float64 rounded once to fp32; W2C rotation and
     translation, then the camera centre -R^T t (used by the SH option only).  20 host floats
-    (GS_CAMERA_FLOATS)."""
+    (GS_CAMERA_FLOATS).  Plain Python arithmetic on the 16 matrix entries: this runs once per frame on
+    the launch path, ahead of the first kernel."""
     W, H = camera._width, camera._height
-    fx = np.float32(0.5 * W / math.tan(camera._FoVx * 0.5))
-    fy = np.float32(0.5 * H / math.tan(camera._FoVy * 0.5))
-    cx = np.float32(W * 0.5)
-    cy = np.float32(H * 0.5)
-    WV = camera.world_view_transform()
-    wv = WV.detach().to(device="cpu", dtype=_F32).numpy()
-    centre = -(wv[:3, :3].astype(np.float64).T @ wv[:3, 3].astype(np.float64))
-    vals = list(wv[:3, :3].reshape(-1)) + list(wv[:3, 3]) + [fx, fy, cx, cy] + list(centre) + [0.0]
-    return (ctypes.c_float * 20)(*[float(v) for v in vals])
+    fx = float(np.float32(0.5 * W / math.tan(camera._FoVx * 0.5)))
+    fy = float(np.float32(0.5 * H / math.tan(camera._FoVy * 0.5)))
+    wv = camera.world_view_transform()
+    if wv.device.type != "cpu" or wv.dtype != _F32:
+        wv = wv.detach().to(device="cpu", dtype=_F32)
+    m = wv.tolist()
+    r0, r1, r2 = m[0], m[1], m[2]
+    tx, ty, tz = r0[3], r1[3], r2[3]
+    return (ctypes.c_float * 20)(r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2], tx, ty, tz,
+                                 fx, fy, float(np.float32(W * 0.5)), float(np.float32(H * 0.5)),
+                                 -(r0[0] * tx + r1[0] * ty + r2[0] * tz), -(r0[1] * tx + r1[1] * ty + r2[1] * tz),
+                                 -(r0[2] * tx + r1[2] * ty + r2[2] * tz), 0.0)
 
 
 def _stream(device) -> ctypes.c_void_p:

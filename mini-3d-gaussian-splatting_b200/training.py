@@ -96,8 +96,9 @@ class GaussianOptimizer:
 
 
 class DensityController:
-    def __init__(self, config: Optional[TrainingConfig] = None):
+    def __init__(self, config: Optional[TrainingConfig] = None, fused: bool = True):
         self.config = config or TrainingConfig()
+        self.fused = fused           # CUDA models: gs_densify_plan / gs_densify_apply instead of tensor ops
 
     def should_densify(self, iteration: int) -> bool:
         c = self.config
@@ -113,6 +114,14 @@ class DensityController:
         if g is None:
             return {"split": 0, "cloned": 0, "pruned": 0, "points": model.get_num_points()}
         th = self.config.densify_grad_threshold
+        if g.is_cuda and self.fused and hasattr(model, "densify_fused"):
+            # one plan + one apply pass on the device; the counts below are those of the sequential formulation
+            # except "pruned", which here counts only originals (a pruned clone/child was never created)
+            n0 = model.get_num_points()
+            r = model.densify_fused(g, th, scene_extent, 0.01, generator=generator)
+            if optimizer is not None:
+                optimizer.rebuild()
+            return {"split": r["split"], "cloned": r["cloned"], "pruned": n0 - r["kept"] - r["split"], "points": r["points"]}
         gn = g.norm(dim=-1)
         sig = model.get_scaling.mean(dim=-1)
         clone_mask = (gn > th) & (sig < 0.01 * scene_extent)

@@ -128,3 +128,49 @@ def test_fused_gradient_sink_equals_autograd_accumulation():
     assert torch.allclose(a.grad_norm_sum, b.grad_norm_sum, rtol=1e-5, atol=1e-9 * scale)
     assert torch.equal(a.vis_count, b.vis_count) and float(a.vis_count.max()) == 3.0
     assert torch.equal(a.max_radii, b.max_radii) and float(a.max_radii.max()) > 0
+
+
+@pytest.mark.gpu
+def test_device_densification_equals_sequential_formulation():
+    """gs_densify_plan / gs_densify_apply against density_and_clone -> density_and_split -> prune (tensor ops)."""
+    n = 20011
+    s = so.scene_aniso(n, 61)
+    g = torch.Generator().manual_seed(7)
+    sc = s["scaling"].clone()
+    sc[: n // 3] = math.log(0.05) + 0.1 * torch.randn(n // 3, 3, generator=g)          # large  -> split candidates
+    sc[n // 3: 2 * n // 3] = math.log(0.004) + 0.1 * torch.randn(n // 3, 3, generator=g)   # small  -> clone candidates
+    op = s["opacity"].clone()
+    op[::7] = -9.0                                         # transparent -> pruned (also as clone copies / children)
+    op[5::11] = 8.0                                        # children's logit is clamped to 6
+    grad = torch.zeros(n, 3)
+    hot = torch.rand(n, generator=g) < 0.6
+    grad[hot] = 1.0 + torch.rand(int(hot.sum()), 3, generator=g)
+    rest = 0.1 * torch.randn(n, 15, 3, generator=g)
+
+    def fresh():
+        m = gb.GaussianModel(device="cuda")
+        m.create_from_tensors(s["xyz"], s["features_dc"], sc, s["rotation"], op, rest)
+        return m
+    th, extent = 0.5, 1.0
+    a, b = fresh(), fresh()
+    gc = grad.cuda()
+    # the sequential path draws randn(k,3) for its k clones; give the fused path the same numbers at the same rows
+    clone_mask = (gc.norm(dim=-1) > th) & (a.get_scaling.mean(dim=-1) < 0.01 * extent)
+    gen = torch.Generator().manual_seed(3)
+    noise_k = torch.randn(int(clone_mask.sum()), 3, generator=torch.Generator().manual_seed(3))
+    noise = torch.zeros(n, 3, device="cuda")
+    noise[clone_mask] = noise_k.cuda()
+    cfg = gb.TrainingConfig(densify_grad_threshold=th)
+    ra = gb.DensityController(cfg, fused=False).densify_and_prune(a, None, extent, grad=gc, generator=gen)
+    rb = b.densify_fused(gc, th, extent, 0.01, noise=noise)
+    assert rb["points"] == ra["points"] == a.get_num_points() == b.get_num_points()
+    assert rb["cloned"] > 1000 and rb["split"] > 1000 and rb["points"] != n
+    for name in ("_features_dc", "_features_rest"):
+        assert torch.equal(getattr(a, name).data, getattr(b, name).data), name
+    for name, tol in (("_xyz", 1e-6), ("_scaling", 1e-6), ("_rotation", 1e-6), ("_opacity", 2e-5)):
+        assert torch.allclose(getattr(a, name).data, getattr(b, name).data, rtol=0, atol=tol), name
+    assert b.denom.shape == (rb["points"], 1) and b.max_radii2D.shape == (rb["points"],)
+    # the controller takes the fused route on CUDA models by default
+    c = fresh()
+    rc = gb.DensityController(cfg).densify_and_prune(c, None, extent, grad=gc, generator=torch.Generator().manual_seed(3))
+    assert rc["points"] == c.get_num_points() and rc["split"] == rb["split"] and rc["cloned"] == rb["cloned"]
