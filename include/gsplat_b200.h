@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 10
+#define GS_ABI_VERSION 11
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -204,6 +204,9 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
  * culling: the reference returns the background ONCE, unclamped, when nothing is visible
  * (renderer.py:74-83) and adds it TWICE otherwise (renderer.py:273 + :359); if counters_dev is not NULL
  * the kernel reads that fact from counters_dev[2] itself and any_visible_host is ignored.
+ * tile_order (optional): a permutation of the tile indices giving the order in which CTAs take tiles
+ * (gs_tile_order on an estimate of the tiles' work -- e.g. the previous frame's tile_consumed -- puts the
+ * heavy tiles first so that light ones fill the last wave); results do not depend on it.
  * Outputs: image [3,H,W], alpha [1,H,W], depth [1,H,W];
  *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue;
  *   tile_consumed [num_tiles] int32 = list entries the tile loaded before all its pixels saturated
@@ -214,19 +217,25 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
 int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
                   const float* splat_rec, const float* bg, int32_t any_visible_host,
-                  const int64_t* counters_dev,
+                  const int64_t* counters_dev, const int32_t* tile_order,
                   float* image, float* alpha, float* depth,
                   float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
                   void* stream);
 
+/* tile_order = a permutation of [0, num_tiles) sorted by decreasing tile_consumed (bucketed by 8 entries). */
+int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, int32_t* tile_order, void* stream);
+
 /* Backward of gs_raster_fwd.  g_image [3,H,W], g_alpha [1,H,W], g_depth [1,H,W] upstream.
  * Gradients are ACCUMULATED (atomic adds) into caller-zeroed g_means2d [n,2], g_conics [n,2,2],
- * g_depths [n], g_colors [n,3], g_opacities [n]. */
+ * g_depths [n], g_colors [n,3], g_opacities [n].
+ * tile_order_scratch (optional, [num_tiles] int32): when given, the tiles are first bucketed by their exact
+ * work (tile_consumed, heaviest first) and taken in that order -- the grid is only a few waves of one-warp
+ * CTAs and the tiles' work varies widely, so the natural order leaves full-size tiles in the last wave. */
 int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
                   const float* splat_rec, const float* bg,
                   const float* alpha, const float* pix_state,
-                  const int32_t* tile_consumed,
+                  const int32_t* tile_consumed, int32_t* tile_order_scratch,
                   const float* g_image, const float* g_alpha, const float* g_depth,
                   float* g_means2d, float* g_conics, float* g_depths,
                   float* g_colors, float* g_opacities,

@@ -218,12 +218,12 @@ __global__ void __launch_bounds__(32, GS_FWD_MINB)
 raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, int any_visible_host, const int64_t* __restrict__ counters_dev,
-                  float* __restrict__ image, float* __restrict__ alpha, float* __restrict__ depth,
+                  const int32_t* __restrict__ tile_order, float* __restrict__ image, float* __restrict__ alpha, float* __restrict__ depth,
                   float4* __restrict__ pix_state, int32_t* __restrict__ n_consumed,
                   int32_t* __restrict__ tile_consumed) {
     __shared__ float4 srec[GS_PREFETCH ? 2 : 1][kBatch * 3];
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;      // any permutation of the tiles
     const int lane = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int py = ty * kTile + (lane >> 1);
@@ -493,7 +493,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, const float* __restrict__ alpha,
                   const float4* __restrict__ pix_state, const int32_t* __restrict__ tile_consumed,
-                  const float* __restrict__ g_image, const float* __restrict__ g_alpha,
+                  const int32_t* __restrict__ tile_order, const float* __restrict__ g_image, const float* __restrict__ g_alpha,
                   const float* __restrict__ g_depth,
                   float* __restrict__ g_means2d, float* __restrict__ g_conics, float* __restrict__ g_depths,
                   float* __restrict__ g_colors, float* __restrict__ g_opac) {
@@ -501,7 +501,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     __shared__ int sid[GS_PREFETCH ? 2 : 1][kBatch];
     __shared__ __align__(16) float red[kBwdGroup * kRedVals * kRedStride + 16];
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;      // any permutation of the tiles
     const int lane = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int py = ty * kTile + (lane >> 1);
@@ -647,6 +647,44 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 #endif
 }
 
+// Longest-first launch order for the backward pass.  The work of a tile is known exactly (tile_consumed,
+// written by the forward) and varies a lot (config[1]: 0..492 entries, mean 312, std 128), while the grid is
+// only ~3.4 waves of one-warp CTAs: in raster order the last wave still holds full-size tiles.  One small
+// block buckets the tiles by consumed/8 (counting sort, heaviest bucket first); CTAs are dispatched in
+// blockIdx order, so the light tiles fill the tail.
+constexpr int kOrderBuckets = 256;
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(int num_tiles, const int32_t* __restrict__ tile_consumed, int32_t* __restrict__ order) {
+    __shared__ int s_cnt[kOrderBuckets];
+    __shared__ int s_off[kOrderBuckets];
+    const int tid = threadIdx.x;
+    if (tid < kOrderBuckets) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int t = tid; t < num_tiles; t += blockDim.x) {
+        const int b = kOrderBuckets - 1 - min(kOrderBuckets - 1, tile_consumed[t] >> 3);
+        atomicAdd(&s_cnt[b], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {                                   // exclusive scan of 256 counts by one warp (8 per lane)
+        int local[kOrderBuckets / 32], sum = 0;
+#pragma unroll
+        for (int q = 0; q < kOrderBuckets / 32; ++q) { local[q] = sum; sum += s_cnt[tid * (kOrderBuckets / 32) + q]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += x;
+        }
+#pragma unroll
+        for (int q = 0; q < kOrderBuckets / 32; ++q) s_off[tid * (kOrderBuckets / 32) + q] = inc - sum + local[q];
+    }
+    __syncthreads();
+    for (int t = tid; t < num_tiles; t += blockDim.x) {
+        const int b = kOrderBuckets - 1 - min(kOrderBuckets - 1, tile_consumed[t] >> 3);
+        order[atomicAdd(&s_off[b], 1)] = t;
+    }
+}
+
 }  // namespace gs
 
 using namespace gs;
@@ -665,8 +703,9 @@ static int check_raster_args(int32_t img_w, int32_t img_h, int32_t tile_size, co
 
 extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, const int32_t* entry_ids,
                              const int32_t* tile_ranges, const float* splat_rec, const float* bg,
-                             int32_t any_visible_host, const int64_t* counters_dev, float* image, float* alpha, float* depth,
-                             float* pix_state, int32_t* n_consumed, int32_t* tile_consumed, void* stream) {
+                             int32_t any_visible_host, const int64_t* counters_dev, const int32_t* tile_order, float* image,
+                             float* alpha, float* depth, float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
+                             void* stream) {
     const int rc = check_raster_args(img_w, img_h, tile_size, "gs_raster_fwd");
     if (rc != GS_OK) return rc;
     GS_REQUIRE(tile_ranges && bg && image && alpha && depth && pix_state && tile_consumed, "NULL array argument");
@@ -676,11 +715,11 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     if (n_consumed) {
         raster_fwd_kernel<true><<<tiles_x * tiles_y, 32, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            counters_dev, image, alpha, depth, (float4*)pix_state, n_consumed, tile_consumed);
+            counters_dev, tile_order, image, alpha, depth, (float4*)pix_state, n_consumed, tile_consumed);
     } else {
         raster_fwd_kernel<false><<<tiles_x * tiles_y, 32, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            counters_dev, image, alpha, depth, (float4*)pix_state, nullptr, tile_consumed);
+            counters_dev, tile_order, image, alpha, depth, (float4*)pix_state, nullptr, tile_consumed);
     }
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
@@ -689,19 +728,33 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
 
 extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, const int32_t* entry_ids,
                              const int32_t* tile_ranges, const float* splat_rec, const float* bg, const float* alpha,
-                             const float* pix_state, const int32_t* tile_consumed, const float* g_image,
-                             const float* g_alpha, const float* g_depth, float* g_means2d, float* g_conics,
-                             float* g_depths, float* g_colors, float* g_opacities, void* stream) {
+                             const float* pix_state, const int32_t* tile_consumed, int32_t* tile_order_scratch,
+                             const float* g_image, const float* g_alpha, const float* g_depth, float* g_means2d,
+                             float* g_conics, float* g_depths, float* g_colors, float* g_opacities, void* stream) {
     const int rc = check_raster_args(img_w, img_h, tile_size, "gs_raster_bwd");
     if (rc != GS_OK) return rc;
     GS_REQUIRE(tile_ranges && bg && alpha && pix_state && tile_consumed && g_image && g_alpha && g_depth && g_means2d &&
                    g_conics && g_depths && g_colors && g_opacities, "NULL array argument");
     DeviceGuard guard(alpha);
     const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
+    if (tile_order_scratch) {
+        tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tiles_x * tiles_y, tile_consumed, tile_order_scratch);
+        GS_CUDA_TRY(cudaGetLastError());
+        count_launches(1);
+    }
     raster_bwd_kernel<<<tiles_x * tiles_y, 32, 0, (cudaStream_t)stream>>>(
         img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
-        (const float4*)pix_state, tile_consumed, g_image, g_alpha, g_depth, g_means2d, g_conics, g_depths, g_colors,
-        g_opacities);
+        (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, g_depth, g_means2d, g_conics,
+        g_depths, g_colors, g_opacities);
+    GS_CUDA_TRY(cudaGetLastError());
+    count_launches(1);
+    return GS_OK;
+}
+
+extern "C" int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, int32_t* tile_order, void* stream) {
+    GS_REQUIRE(num_tiles > 0 && tile_consumed && tile_order, "bad arguments");
+    DeviceGuard guard(tile_consumed);
+    tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, tile_consumed, tile_order);
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
     return GS_OK;

@@ -250,6 +250,13 @@ class _RasterizeFn(torch.autograd.Function):
         n_consumed = torch.empty((H, W), dtype=_I32, device=dev) if track else None
         tile_consumed = torch.empty((tiles,), dtype=_I32, device=dev)
         tile_ranges = torch.empty((tiles, 2), dtype=_I32, device=dev)
+        # launch order of the tiles: heaviest first, by the work they had in the previous frame of this size
+        # (any permutation gives the same image; a good one keeps full-size tiles out of the last wave)
+        bins.tile_order = None
+        prev = bins.prev_consumed
+        if prev is not None and prev.numel() == tiles and prev.device == dev:
+            bins.tile_order = torch.empty(tiles, dtype=_I32, device=dev)
+            check(lib.gs_tile_order(tiles, ptr(prev), ptr(bins.tile_order), stream), "gs_tile_order")
 
         def enqueue(num_sorted, d_size, counters_dev):
             entry_ids = torch.empty(max(d_size, 1), dtype=_I32, device=dev)
@@ -261,7 +268,7 @@ class _RasterizeFn(torch.autograd.Function):
                                       ptr(entry_ids), ptr(tile_ranges), None, counters_dev, stream), "gs_bin_sort")
             with _timed("raster_fwd", dev):
                 check(lib.gs_raster_fwd(W, H, T, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
-                                        int(bins.num_vis > 0) if counters_dev is None else 0, counters_dev,
+                                        int(bins.num_vis > 0) if counters_dev is None else 0, counters_dev, ptr(bins.tile_order),
                                         ptr(image), ptr(alpha), ptr(depth), ptr(pix_state),
                                         ptr(n_consumed), ptr(tile_consumed), stream), "gs_raster_fwd")
             return entry_ids
@@ -278,6 +285,7 @@ class _RasterizeFn(torch.autograd.Function):
             entry_ids = enqueue(bins.num_sorted, bins.D, None)
         entry_ids = entry_ids[:bins.D]
         bins.entry_ids, bins.tile_ranges = entry_ids, tile_ranges
+        bins.renderer_consumed[(dev.index, W, H)] = tile_consumed
 
         ctx.meta = meta
         ctx.set_materialize_grads(False)
@@ -312,9 +320,10 @@ class _RasterizeFn(torch.autograd.Function):
                 return g.contiguous()
 
             gi, ga, gd = dense(g_image, 3), dense(g_alpha, 1), dense(g_depth, 1)
+            order = torch.empty(tile_consumed.numel(), dtype=_I32, device=dev)      # heaviest tiles first (exact work)
             with _timed("raster_bwd", dev):
                 check(lib.gs_raster_bwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), ptr(alpha),
-                                        ptr(pix_state), ptr(tile_consumed), ptr(gi), ptr(ga), ptr(gd),
+                                        ptr(pix_state), ptr(tile_consumed), ptr(order), ptr(gi), ptr(ga), ptr(gd),
                                         ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                                         _stream(dev)), "gs_raster_bwd")
         return None, None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None
@@ -332,6 +341,9 @@ class _FrameBins:
             slot = (torch.empty(3, dtype=_I64).pin_memory(), torch.cuda.Event())
             renderer._readback[device.index] = slot
         self._host, self._event = slot
+        self.renderer_consumed = renderer._tile_consumed
+        self.prev_consumed = None
+        self.tile_order = None
         self.num_sorted = self.D = self.num_vis = None
         self.entry_ids = self.tile_ranges = None
 
@@ -389,6 +401,7 @@ class GaussianRenderer:
         self.optimistic_binning = True
         self._d_cap: Dict[int, Optional[int]] = {}
         self._readback: Dict[int, tuple] = {}
+        self._tile_consumed: Dict[tuple, torch.Tensor] = {}     # last frame's per-tile work per (device, W, H)
         _lib.load()   # fail at construction, not at first render, if the extension is missing
 
     def accumulate_into(self, sink):
@@ -493,6 +506,7 @@ class GaussianRenderer:
         num_tiles = tiles_x * tiles_y
         stream = _stream(device)
         bins = _FrameBins(self, device)
+        bins.prev_consumed = self._tile_consumed.get((device.index, W, H))
         # 0 = the flat counting sort.  3 (blocked two-level sort, coalesced final stores) is bit-identical and
         # measured no faster (385 vs 376 us at config[1]); it needs rectangles of at most 8 tiles per side
         algo = self.bin_algo if self.bin_algo else 1

@@ -40,3 +40,6 @@ per = timer.summary_ms()
 print("lib:", os.environ.get("GSPLAT_B200_LIB", "default"))
 print("  " + "  ".join(f"{k}={sum(v)/len(v)*1000:.1f}us" for k, v in per.items()))
 print("  checksums: " + " ".join(f"{c:.9g}" for c in chk))
+tc = rd._last_debug["tile_consumed"].float()
+print(f"  tile_consumed: min {float(tc.min()):.0f} mean {float(tc.mean()):.1f} max {float(tc.max()):.0f} std {float(tc.std()):.1f}; "
+      f"sum of the top 2368 / total = {float(tc.sort(descending=True).values[:2368].sum() / tc.sum()):.3f}")
