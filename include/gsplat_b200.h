@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 11
+#define GS_ABI_VERSION 12
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -222,8 +222,10 @@ int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
                   void* stream);
 
-/* tile_order = a permutation of [0, num_tiles) sorted by decreasing tile_consumed (bucketed by 8 entries). */
-int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, int32_t* tile_order, void* stream);
+/* tile_order = a permutation of [0, num_tiles) sorted by decreasing work estimate (bucketed by 8 entries):
+ * tile_consumed when given (what a forward measured), else the tiles' list lengths from tile_ranges. */
+int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, const int32_t* tile_ranges, int32_t* tile_order,
+                  void* stream);
 
 /* Backward of gs_raster_fwd.  g_image [3,H,W], g_alpha [1,H,W], g_depth [1,H,W] upstream.
  * Gradients are ACCUMULATED (atomic adds) into caller-zeroed g_means2d [n,2], g_conics [n,2,2],

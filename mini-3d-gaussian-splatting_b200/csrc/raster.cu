@@ -654,16 +654,22 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 // blockIdx order, so the light tiles fill the tail.
 constexpr int kOrderBuckets = 256;
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(int num_tiles, const int32_t* __restrict__ tile_consumed, int32_t* __restrict__ order) {
+tile_order_kernel(int num_tiles, const int32_t* __restrict__ tile_consumed, const int2* __restrict__ tile_ranges,
+                  int32_t* __restrict__ order) {
     __shared__ int s_cnt[kOrderBuckets];
     __shared__ int s_off[kOrderBuckets];
     const int tid = threadIdx.x;
     if (tid < kOrderBuckets) s_cnt[tid] = 0;
     __syncthreads();
-    for (int t = tid; t < num_tiles; t += blockDim.x) {
-        const int b = kOrderBuckets - 1 - min(kOrderBuckets - 1, tile_consumed[t] >> 3);
-        atomicAdd(&s_cnt[b], 1);
-    }
+    // work estimate of a tile: what it consumed (exact, backward), or -- before the forward has run -- the length of
+    // its list: a short list IS the work, a long one saturates somewhere, so long lists only need to come first
+    auto bucket = [&](int t) {
+        int work;
+        if (tile_consumed) work = tile_consumed[t];
+        else { const int2 r = tile_ranges[t]; work = r.y - r.x; }
+        return kOrderBuckets - 1 - min(kOrderBuckets - 1, work >> 3);
+    };
+    for (int t = tid; t < num_tiles; t += blockDim.x) atomicAdd(&s_cnt[bucket(t)], 1);
     __syncthreads();
     if (tid < 32) {                                   // exclusive scan of 256 counts by one warp (8 per lane)
         int local[kOrderBuckets / 32], sum = 0;
@@ -679,10 +685,7 @@ tile_order_kernel(int num_tiles, const int32_t* __restrict__ tile_consumed, int3
         for (int q = 0; q < kOrderBuckets / 32; ++q) s_off[tid * (kOrderBuckets / 32) + q] = inc - sum + local[q];
     }
     __syncthreads();
-    for (int t = tid; t < num_tiles; t += blockDim.x) {
-        const int b = kOrderBuckets - 1 - min(kOrderBuckets - 1, tile_consumed[t] >> 3);
-        order[atomicAdd(&s_off[b], 1)] = t;
-    }
+    for (int t = tid; t < num_tiles; t += blockDim.x) order[atomicAdd(&s_off[bucket(t)], 1)] = t;
 }
 
 }  // namespace gs
@@ -738,7 +741,7 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     DeviceGuard guard(alpha);
     const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
     if (tile_order_scratch) {
-        tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tiles_x * tiles_y, tile_consumed, tile_order_scratch);
+        tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tiles_x * tiles_y, tile_consumed, nullptr, tile_order_scratch);
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
     }
@@ -751,10 +754,11 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     return GS_OK;
 }
 
-extern "C" int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, int32_t* tile_order, void* stream) {
-    GS_REQUIRE(num_tiles > 0 && tile_consumed && tile_order, "bad arguments");
-    DeviceGuard guard(tile_consumed);
-    tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, tile_consumed, tile_order);
+extern "C" int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, const int32_t* tile_ranges, int32_t* tile_order,
+                             void* stream) {
+    GS_REQUIRE(num_tiles > 0 && (tile_consumed || tile_ranges) && tile_order, "bad arguments");
+    DeviceGuard guard(tile_order);
+    tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, tile_consumed, (const int2*)tile_ranges, tile_order);
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
     return GS_OK;

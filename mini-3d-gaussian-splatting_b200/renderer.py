@@ -252,11 +252,12 @@ class _RasterizeFn(torch.autograd.Function):
         tile_ranges = torch.empty((tiles, 2), dtype=_I32, device=dev)
         # launch order of the tiles: heaviest first, by the work they had in the previous frame of this size
         # (any permutation gives the same image; a good one keeps full-size tiles out of the last wave)
-        bins.tile_order = None
-        prev = bins.prev_consumed
-        if prev is not None and prev.numel() == tiles and prev.device == dev:
-            bins.tile_order = torch.empty(tiles, dtype=_I32, device=dev)
-            check(lib.gs_tile_order(tiles, ptr(prev), ptr(bins.tile_order), stream), "gs_tile_order")
+        bins.tile_order = torch.empty(tiles, dtype=_I32, device=dev)
+        prev = bins.prev_consumed if bins.fwd_order == "previous" else None
+        if prev is not None and (prev.numel() != tiles or prev.device != dev):
+            prev = None
+        if prev is not None:
+            check(lib.gs_tile_order(tiles, ptr(prev), None, ptr(bins.tile_order), stream), "gs_tile_order")
 
         def enqueue(num_sorted, d_size, counters_dev):
             entry_ids = torch.empty(max(d_size, 1), dtype=_I32, device=dev)
@@ -266,6 +267,8 @@ class _RasterizeFn(torch.autograd.Function):
                 check(lib.gs_bin_sort(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
                                       ptr(bins.depth_keys), tiles_x, tiles, int(bins.algo), ptr(ws), ws.numel(),
                                       ptr(entry_ids), ptr(tile_ranges), None, counters_dev, stream), "gs_bin_sort")
+            if prev is None:                      # this frame's list lengths, available as soon as the binning has run
+                check(lib.gs_tile_order(tiles, None, ptr(tile_ranges), ptr(bins.tile_order), stream), "gs_tile_order")
             with _timed("raster_fwd", dev):
                 check(lib.gs_raster_fwd(W, H, T, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
                                         int(bins.num_vis > 0) if counters_dev is None else 0, counters_dev, ptr(bins.tile_order),
@@ -344,6 +347,7 @@ class _FrameBins:
         self.renderer_consumed = renderer._tile_consumed
         self.prev_consumed = None
         self.tile_order = None
+        self.fwd_order = renderer.fwd_tile_order
         self.num_sorted = self.D = self.num_vis = None
         self.entry_ids = self.tile_ranges = None
 
@@ -402,6 +406,9 @@ class GaussianRenderer:
         self._d_cap: Dict[int, Optional[int]] = {}
         self._readback: Dict[int, tuple] = {}
         self._tile_consumed: Dict[tuple, torch.Tensor] = {}     # last frame's per-tile work per (device, W, H)
+        # work estimate behind the forward's tile launch order: "ranges" = this frame's list lengths,
+        # "previous" = what the tiles consumed in the previous frame of the same size (falls back to "ranges")
+        self.fwd_tile_order = "ranges"
         _lib.load()   # fail at construction, not at first render, if the extension is missing
 
     def accumulate_into(self, sink):

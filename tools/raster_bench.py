@@ -14,6 +14,7 @@ W, H = 1920, 1080
 dev = torch.device("cuda", 0)
 model = gb.GaussianModel(device=dev); model.create_from_random(N, 1.0, seed=0)
 rd = gb.GaussianRenderer()
+rd.fwd_tile_order = os.environ.get("GS_FWD_ORDER", rd.fwd_tile_order)
 st = gb.RenderSettings(H, W, torch.zeros(3, device=dev))
 cam = gb.Camera.look_at_origin_c0(W, H)
 rmod = import_module("mini-3d-gaussian-splatting_b200.renderer")
@@ -37,7 +38,7 @@ for r in range(reps + 2):
                float(model._features_dc.grad.double().abs().sum()))
 rmod.stage_timer.active = None
 per = timer.summary_ms()
-print("lib:", os.environ.get("GSPLAT_B200_LIB", "default"))
+print("lib:", os.environ.get("GSPLAT_B200_LIB", "default"), "fwd order:", rd.fwd_tile_order)
 print("  " + "  ".join(f"{k}={sum(v)/len(v)*1000:.1f}us" for k, v in per.items()))
 print("  checksums: " + " ".join(f"{c:.9g}" for c in chk))
 tc = rd._last_debug["tile_consumed"].float()

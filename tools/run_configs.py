@@ -53,6 +53,7 @@ if "3" in which:
     m = gb.GaussianModel(device=dev)
     m.create_from_random(1_000_000, 1.0, seed=0)
     rd = gb.GaussianRenderer()
+    rd.fwd_tile_order = os.environ.get("GS_FWD_ORDER", rd.fwd_tile_order)
     st = gb.RenderSettings(H, W, torch.zeros(3, device=dev))
     w = [t.to(dev) for t in so.loss_weights(H, W)]
     buf = mv.FlatGradBuffer(m)
