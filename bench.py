@@ -376,6 +376,10 @@ def main():
                 "frac": kernels[top]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "note": ("the compositing kernels are FP32/MUFU-issue bound, not HBM bound (SURVEY 8d): see `issue`"
                          if evals else "")}
+    frame_bytes = float(sum(alg.values()))
+    roofline["frame"] = {"alg_bytes": frame_bytes, "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
+                         "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                         "note": "all stages' algorithmic bytes / step time: the whole frame against the HBM roofline"}
     if evals:
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         lane_roof = 148 * 128 * sm_clock * 1e6
