@@ -123,7 +123,9 @@ int gs_project_fwd(int64_t n,
  *   (replaces the `.grad +=` that autograd would otherwise run per tensor).
  * stat_* (all NULL, or all non-NULL, each [n]): densification statistics fused into this pass; for
  *   every splat with stat_vis[i] != 0:  stat_grad_norm[i] += |g_means2d[i]|, stat_count[i] += 1,
- *   stat_max_radii[i] = max(stat_max_radii[i], stat_radii[i]).  These are the buffers the reference
+ *   stat_max_radii[i] = max(stat_max_radii[i], stat_radii[i]) when accumulate != 0; with accumulate == 0 the
+ *   three statistics are WRITTEN for every splat (zeros where not visible), like the gradients -- so the
+ *   first view of a step initialises the whole buffer and nothing has to be zeroed.  These are the buffers the reference
  *   allocates as xyz_gradient_accum / denom / max_radii2D (gaussian_model.py:29-31). */
 int gs_project_bwd(int64_t n,
                    const float* xyz,

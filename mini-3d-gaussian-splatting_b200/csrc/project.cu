@@ -421,10 +421,20 @@ project_bwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     if (i >= n) return;
 
     const float2 gm = g_means2d[i];
-    if (stats.grad_norm != nullptr && stats.vis[i]) {
-        stats.grad_norm[i] += sqrtf(gm.x * gm.x + gm.y * gm.y);
-        stats.count[i] += 1.0f;
-        stats.max_radii[i] = fmaxf(stats.max_radii[i], stats.radii[i]);
+    if (stats.grad_norm != nullptr) {
+        const bool v = stats.vis[i] != 0;
+        const float gn = v ? sqrtf(gm.x * gm.x + gm.y * gm.y) : 0.f, c = v ? 1.0f : 0.f, r = v ? stats.radii[i] : 0.f;
+        if (acc) {
+            if (v) {
+                stats.grad_norm[i] += gn;
+                stats.count[i] += c;
+                stats.max_radii[i] = fmaxf(stats.max_radii[i], r);
+            }
+        } else {                                    // first view of a step: initialises the statistics as well
+            stats.grad_norm[i] = gn;
+            stats.count[i] = c;
+            stats.max_radii[i] = r;
+        }
     }
     const float4 gq = g_conics[i];
     const float gz_in = g_depths[i];

@@ -98,8 +98,12 @@ class FlatGradBuffer:
                      "ptrs": (ctypes.c_uint64 * len(ptrs))(*ptrs), "multicast": mc}
         return t
 
-    def install(self) -> None:
-        self.storage.zero_()
+    def install(self, zero: bool = True) -> None:
+        """Point the parameters' `.grad` at the buffer.  `zero=False` when the first view of the step is going to
+        overwrite every element anyway (gs_project_bwd in write mode: `fresh`)."""
+        if zero:
+            self.storage.zero_()
+        self.fresh = not zero
         for name, v in zip(PARAM_ORDER, self.views):
             getattr(self.model, name).grad = v
         rest = getattr(self.model, "_features_rest", None)
@@ -140,12 +144,14 @@ def multiview_step(model, renderer, cameras: Sequence, settings, loss_fn: Callab
     reference allocates but never fills (gaussian_model.py:29-31).
     """
     buf = buffer if buffer is not None else FlatGradBuffer(model)
-    buf.install()
     ids = list(view_ids) if view_ids is not None else list(range(len(cameras)))
     losses = []
     # B200 renderer: the projection backward adds gradients and statistics into `buf` itself
     # (gs_project_bwd accumulate + stat_*); any other renderer goes through autograd accumulation.
-    fused = hasattr(renderer, "accumulate_into") and getattr(renderer, "sh_degree", 0) == 0
+    fused = (hasattr(renderer, "accumulate_into") and getattr(renderer, "sh_degree", 0) == 0
+             and buf.flat.is_cuda and getattr(model, "get_num_points", lambda: 0)() == buf.n)
+    # fused path with at least one view: the first view's backward writes the whole buffer, so it is not zeroed
+    buf.install(zero=not (fused and len(ids) > 0))
     if fused:
         with renderer.accumulate_into(buf):
             for cam, vid in zip(cameras, ids):

@@ -170,13 +170,16 @@ class _ProjectFn(torch.autograd.Function):
             # densification statistics in the same pass; autograd then has nothing left to accumulate
             g_xyz, g_feat, g_scaling, g_rotation, g_opacity = sink.views
             radii, vis = ctx.stat_inputs
+            # the first view of a step WRITES gradients and statistics (the buffer needs no zero-fill), later views add
+            accumulate = 0 if getattr(sink, "fresh", False) else 1
+            sink.fresh = False
             with _timed("project_bwd", dev):
                 check(lib.gs_project_bwd(
                     n, ptr(xyz), ptr(scaling), ptr(rotation), None, ptr(opacity), 1,
                     ptr(feat_src), meta.feat_stride, None, 0, 0, meta.cam,
                     ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                     ptr(g_xyz), ptr(g_scaling), ptr(g_rotation), None, ptr(g_opacity),
-                    ptr(g_feat), 3, None, 0, 1,
+                    ptr(g_feat), 3, None, 0, accumulate,
                     ptr(radii), ptr(vis), ptr(sink.grad_norm_sum), ptr(sink.vis_count), ptr(sink.max_radii),
                     _stream(dev)), "gs_project_bwd")
             return (None,) * 8
@@ -504,6 +507,11 @@ class GaussianRenderer:
         if (sink is not None and meta.param_mode and self.sh_degree == 0 and sink.n == n and feat_src.shape[1] == 1
                 and torch.is_grad_enabled()):
             meta.sink = sink
+        elif sink is not None and getattr(sink, "fresh", False):
+            # the caller skipped the zero-fill expecting this view to overwrite the buffer, but the view cannot take
+            # the sink path: gradients will arrive through autograd's `+=`, which needs zeros
+            sink.storage.zero_()
+            sink.fresh = False
 
         (means2d, conics, depths, colors, opac, radii, vis, tiles_touched, tile_rect, depth_keys,
          rec) = _ProjectFn.apply(meta, xyz, scaling, rotation, cov3d, opacity, feat_src, rest)
