@@ -3,20 +3,23 @@
 // Reference semantics: the pixel loop and epilogue of GaussianRenderer._tile_rasterization,
 // src/core/renderer.py:300-367.
 //
-// Both kernels are bound by instruction issue, not by HBM (ncu, profiles/r1_v1_*: DRAM 0.6 %,
-// issue slots 81-90 % busy): a tile saturates after a few hundred of its thousands of list
-// entries, so ~0.3 GB moves while ~6e8 pixel x splat evaluations execute.  The design therefore
-// minimises instructions per evaluation:
-//   * one warp per tile, each lane owns a 1x8 pixel strip (16 rows x 2 strips): the per-entry
-//     work (shared-memory broadcast of the 44-byte record, the dy terms, loop control) is
-//     amortised over 8 evaluations, 8 independent dependency chains hide FP32/MUFU latency, and no
-//     block-wide barrier exists -- only __syncwarp;
-//   * branch-free evaluation: the splat weight is one MUFU.EX2 on a quadratic form whose
-//     coefficients were pre-multiplied by -0.5*log2(e) when project_fwd packed the record, and the
-//     skip / termination rules of the reference are predicates on the accumulation, not branches;
-//   * backward: each lane pre-sums its 8 pixels, then the 10 per-splat sums are reduced across the
-//     warp through a padded shared-memory transpose (10 STS + 11 LDS per lane instead of 50
-//     shuffles) and leave as ONE vector atomic instruction (lanes 0..9 -> 10 addresses).
+// Both kernels are bound by the FP32 FMA pipe, not by HBM (ncu, profiles/r1_v6_*: DRAM < 2 %, FMA pipe
+// 61-65 % busy with math_pipe_throttle the top stall): a tile saturates after a few hundred of its
+// thousands of list entries, so ~0.3 GB moves while ~6e8 pixel x splat evaluations execute.  The design
+// therefore minimises instructions -- FMA-pipe instructions first -- per evaluation:
+//   * one warp per tile, each lane owns a 1x8 pixel strip (16 rows x 2 strips) kept as 4 packed fp32 pairs
+//     (FFMA2 / FMUL2 / FADD2): the per-entry work (shared-memory broadcast of the 48-byte record, the dy
+//     terms, loop control) is amortised over 8 evaluations, 4 independent dependency chains hide FP32/MUFU
+//     latency, and no block-wide barrier exists -- only __syncwarp;
+//   * branch-free evaluation: the splat weight is one MUFU.EX2 on a quadratic form whose coefficients were
+//     pre-multiplied by -0.5*log2(e) when project_fwd packed the record; per batch of 32 entries a fast
+//     path drops both clamps of the reference (identities for records flagged `regular`) and folds the
+//     two skip rules into the weight itself (see eval_pair);
+//   * backward: each lane pre-sums its 8 pixels, then the 10 per-splat sums are reduced across the warp
+//     through a padded shared-memory transpose (10 STS + 3 LDS.128 per lane instead of 50 shuffles) and
+//     leave as ONE vector atomic instruction (lanes 0..9 -> 10 addresses);
+//   * tiles are taken longest-first (tile_order_kernel): the grids are ~3 waves of one-warp CTAs and the
+//     work per tile varies by 40 %, so raster order would leave full-size tiles in the last wave.
 //
 // Accuracy of the weight: ex2.approx on the pre-scaled form differs from the reference's
 // exp(-0.5*s) by <= ~2e-7 relative -- the same size as the error of an "accurate" expf, whose own
@@ -32,9 +35,6 @@ namespace gs {
 #endif
 #ifndef GS_BWD_MINB
 #define GS_BWD_MINB 16
-#endif
-#ifndef GS_CHAIN_PRED
-#define GS_CHAIN_PRED 1
 #endif
 #ifndef GS_BWD_GROUP
 #define GS_BWD_GROUP 2                 // list entries whose arithmetic runs between two warp barriers (backward)
@@ -370,12 +370,8 @@ __device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id
     if (lane < kRedVals) {
         const float total = s + s2 + s3;
         float* dst = out.base + (int64_t)id * out.stride;
-#ifdef GS_EXP_NOATOM     // timing experiment only (wrong results)
-        if (total == 123.456f) *dst = total;
-#else
         atomicAdd(dst, total);
         if (lane == 3) atomicAdd(dst + 1, total);      // Q01 and Q10 enter s symmetrically
-#endif
     }
 }
 
@@ -445,13 +441,6 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
     const float hs = kLn2 * op;                         // dL/ds' = ln2 * op * w * dL/da
     const float Sh = hs * (kFast ? Sop_all : (s_h.x + s_h.y)), Sx = hs * (s_x.x + s_x.y), Sxx = hs * (s_xx.x + s_xx.y);
     const float dySh = dy * Sh;
-#ifdef GS_EXP_NORED      // timing experiment only (wrong results): no cross-lane reduction
-    {
-        const float k = Sh + Sx + Sxx + dySh + Sop + (s_z.x + s_z.y) + (s_cr.x + s_cr.y) + (s_cg.x + s_cg.y) + (s_cb.x + s_cb.y);
-        if (k == 123.456f) rb[lane] = k;
-        return;
-    }
-#endif
     rb[0 * kRedStride + lane] = -fmaf(2.f * r0.z, Sx, r0.w * dySh);             // g_mx
     rb[1 * kRedStride + lane] = -fmaf(2.f * r1.x, dySh, r0.w * Sx);             // g_my
     rb[2 * kRedStride + lane] = kNegHalfLog2e * Sxx;                            // g_Q00
@@ -479,12 +468,10 @@ __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane,
         for (int g = 0; g < kBwdGroup; ++g)
             bwd_entry<kFast>(srec + (j + g) * 3, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA,
                              out.red + g * (kRedVals * kRedStride));
-#ifndef GS_EXP_NORED
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < kBwdGroup; ++g) reduce_finish(out, g, out.sid[j + g], lane);
         __syncwarp();
-#endif
     }
 }
 
