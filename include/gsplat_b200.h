@@ -212,7 +212,7 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
  * Outputs: image [3,H,W], alpha [1,H,W], depth [1,H,W];
  *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue;
  *   tile_consumed [num_tiles] int32 = list entries the tile loaded before all its pixels saturated
- *   (granularity: batches of 32); n_consumed [H*W] int32 (optional, may be NULL) = entries each
+ *   (granularity: 8 entries); n_consumed [H*W] int32 (optional, may be NULL) = entries each
  *   pixel walked up to and including the one that terminated it -- a debug/parity output that
  *   selects a kernel variant with one extra predicated move per evaluation.
  * ------------------------------------------------------------------------------------- */
