@@ -579,7 +579,32 @@ def test_odd_splat_count_keeps_vector_accesses_aligned():
 # ----------------------------------------------------------------------------------------------
 # (6) optimistic binning: device-side sizes with a capacity from the previous frame
 # ----------------------------------------------------------------------------------------------
-def test_optimistic_binning_equals_exact_path_and_survives_overflow():
+def test_optimistic_binning_with_nothing_visible_after_a_normal_frame():
+    """Second frame of a renderer (optimistic path, device-side sizes) sees zero visible splats: background once,
+    zero alpha, zero gradients -- the same contract as the exact path (renderer.py:74-83)."""
+    import gsplat_b200 as gb
+    s = so.scene_aniso(500, 5)
+    s["scaling"] = s["scaling"] + math.log(3.0)
+    m = util.cuda_model_from_params(s)
+    rd = gb.GaussianRenderer()
+    bg = torch.tensor([0.2, 1.5, -0.25])
+    st = gb.RenderSettings(32, 48, bg)
+    first = rd.render(gb.Camera.look_at_origin_c0(48, 32), m, st)
+    assert int(first["visibility_filter"].sum()) > 0 and rd._d_cap[0] is not None
+    behind = torch.eye(4)
+    behind[2, 3] = -30.0                                     # the whole scene lies behind this camera
+    out = rd.render(gb.Camera(48, 32, math.radians(60), world_view=behind), m, st)
+    assert int(out["visibility_filter"].sum()) == 0 and rd.last_stats["tile_pairs"] == 0
+    assert torch.equal(out["image"].cpu(), bg.view(3, 1, 1).repeat(1, 32, 48))
+    assert float(out["alpha"].abs().max()) == 0 and float(out["depth"].abs().max()) == 0
+    (out["image"].sum() + out["alpha"].sum() + out["depth"].sum()).backward()
+    assert float(m._xyz.grad.abs().max()) == 0 and float(m._opacity.grad.abs().max()) == 0
+    again = rd.render(gb.Camera.look_at_origin_c0(48, 32), m, st)          # and back: capacity 4096 still fits or falls back
+    assert torch.equal(again["image"], first["image"])
+
+
+@pytest.mark.parametrize("algo", [1, 3])
+def test_optimistic_binning_equals_exact_path_and_survives_overflow(algo):
     import gsplat_b200 as gb
     s = so.scene_aniso(6000, 91)
     s["scaling"] = s["scaling"] + math.log(2.5)
@@ -598,6 +623,7 @@ def test_optimistic_binning_equals_exact_path_and_survives_overflow():
     exact = gb.GaussianRenderer()
     exact.optimistic_binning = False
     opt = gb.GaussianRenderer()
+    exact.bin_algo = opt.bin_algo = algo
     assert opt.optimistic_binning
     for i, cam in enumerate(cams):
         a = frame(exact, cam)
