@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 12
+#define GS_ABI_VERSION 13
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -196,8 +196,24 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
                 int32_t tiles_x, int32_t num_tiles, int32_t algo,
                 void* workspace, int64_t workspace_bytes,
                 int32_t* entry_ids, int32_t* tile_ranges, uint64_t* entry_keys,
-                const int64_t* counters_dev,
+                const int64_t* counters_dev, int32_t list_cap,
                 void* stream);
+
+/* Truncated tile lists (flat counting sort only).  With list_cap > 0 gs_bin_sort stores only the first list_cap
+ * entries of every tile's list (tile_ranges still describe the complete lists); gs_raster_fwd, given the same
+ * list_cap, composites from that prefix and flags a tile that reaches the end of its stored prefix with pixels
+ * still alive (tile_flags[t] = 1, *flag_count += 1).  gs_bin_complete then stores the remaining entries of the
+ * flagged tiles -- it needs gs_bin_sort's workspace untouched -- and gs_raster_fwd with rerun != 0 composites the
+ * flagged tiles again from their complete lists.  Both completion calls are meant to be enqueued unconditionally:
+ * every CTA returns at once when *flag_count == 0.  The result is identical to list_cap = 0; what is saved are
+ * the scattered stores of entries no pixel consumes (on config[1]: > 70 % of the 26 M). */
+int gs_bin_complete(int64_t n, int64_t num_sorted, int64_t d,
+                    const int32_t* sorted_ids, const int64_t* offsets, const uint16_t* tile_rect,
+                    int32_t tiles_x, int32_t num_tiles,
+                    const void* workspace, int64_t workspace_bytes,
+                    int32_t list_cap, const uint8_t* tile_flags, const int32_t* flag_count,
+                    int32_t* entry_ids, const int64_t* counters_dev,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Stage R: 16x16-tile front-to-back compositing.
@@ -209,6 +225,8 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
  * tile_order (optional): a permutation of the tile indices giving the order in which CTAs take tiles
  * (gs_tile_order on an estimate of the tiles' work -- e.g. the previous frame's tile_consumed -- puts the
  * heavy tiles first so that light ones fill the last wave); results do not depend on it.
+ * list_cap / tile_flags / flag_count / rerun: truncated lists, see gs_bin_complete (list_cap <= 0: complete lists,
+ * the three may be NULL / 0).
  * Outputs: image [3,H,W], alpha [1,H,W], depth [1,H,W];
  *   saved for backward: pix_state [H*W,4] = {C_r, C_g, C_b, Dsum} before the epilogue;
  *   tile_consumed [num_tiles] int32 = list entries the tile loaded before all its pixels saturated
@@ -220,6 +238,7 @@ int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
                   const float* splat_rec, const float* bg, int32_t any_visible_host,
                   const int64_t* counters_dev, const int32_t* tile_order,
+                  int32_t list_cap, uint8_t* tile_flags, int32_t* flag_count, int32_t rerun,
                   float* image, float* alpha, float* depth,
                   float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
                   void* stream);

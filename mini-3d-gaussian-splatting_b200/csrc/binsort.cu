@@ -147,6 +147,17 @@ struct BinSizes {
     int64_t d_capacity;
     const int64_t* dev;             // counters {num_sorted, D, visible} or NULL
 };
+// Truncated tile lists (gs_bin_sort list_cap / gs_bin_complete).  On config[1] a tile consumes at most ~500 of
+// the ~3 200 entries of its list before all its pixels saturate, and the scattered stores are what the
+// binning costs: the first pass therefore stores only the first `limit` entries of every tile, the compositing
+// kernel flags the (rare) tile that reaches the end of its stored prefix with pixels still alive, and a
+// completion pass -- enqueued unconditionally, every CTA of which returns at once when nothing is flagged --
+// stores the rest for the flagged tiles before those tiles are composited again.
+struct ListCap {
+    uint32_t limit;                 // first pass: store entries with in-tile index < limit
+    const uint8_t* tile_flags;      // completion pass: tiles to complete
+    const int32_t* flag_count;      // completion pass: number of flagged tiles (NULL in the first pass)
+};
 __device__ __forceinline__ bool resolve_sizes(const BinSizes& z, int64_t& num_sorted) {
     num_sorted = z.num_sorted;
     if (z.dev != nullptr) {
@@ -378,12 +389,13 @@ scatter_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int
                const uint8_t* __restrict__ local_pos, const uint16_t* __restrict__ base16,
                const uint32_t* __restrict__ super_base, const uint32_t* __restrict__ tile_start,
                const uint32_t* __restrict__ depth_keys, int32_t* __restrict__ entry_ids,
-               uint64_t* __restrict__ entry_keys) {
+               uint64_t* __restrict__ entry_keys, ListCap cap) {
     const int lane = threadIdx.x & 31;
     const int64_t j0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     int64_t num_sorted;
     if (!resolve_sizes(sizes, num_sorted)) return;
     if (j0 >= num_sorted) return;
+    if (cap.flag_count != nullptr && *cap.flag_count == 0) return;        // completion pass with nothing to complete
     const int64_t j = j0 + lane;
     int id = 0, cnt = 0;
     long long off = 0;
@@ -419,7 +431,14 @@ scatter_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int
                 const int row = k / s_w;
                 t = s_origin + row * tiles_x + (k - row * s_w);
             }
-            const uint32_t pos = tile_start[t] + sb[t] + (uint32_t)b16[t] + (uint32_t)lp[k];
+            // truncated lists: the first pass stores a tile's first `limit` entries only; the completion pass
+            // stores the rest, for the tiles the compositing kernel flagged
+            const uint32_t before = sb[t] + (uint32_t)b16[t];                         // pairs of tile t in earlier chunks
+            if (cap.flag_count == nullptr ? before >= cap.limit : cap.tile_flags[t] == 0) continue;
+            const uint32_t in_tile = before + (uint32_t)lp[k];                        // index inside tile t's list
+            const bool store = cap.flag_count == nullptr ? in_tile < cap.limit : in_tile >= cap.limit;
+            if (!store) continue;
+            const uint32_t pos = tile_start[t] + in_tile;
             entry_ids[pos] = s_id;
             if (entry_keys) entry_keys[pos] = ((uint64_t)(uint32_t)t << 32) | s_dk;
         }
@@ -833,7 +852,8 @@ extern "C" int gs_bin_prepare(int64_t n, const uint32_t* depth_keys, const int32
 extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32_t* sorted_ids, const int64_t* offsets,
                            const uint16_t* tile_rect, const uint32_t* depth_keys, int32_t tiles_x, int32_t num_tiles,
                            int32_t algo, void* workspace, int64_t workspace_bytes, int32_t* entry_ids,
-                           int32_t* tile_ranges, uint64_t* entry_keys, const int64_t* counters_dev, void* stream) {
+                           int32_t* tile_ranges, uint64_t* entry_keys, const int64_t* counters_dev, int32_t list_cap,
+                           void* stream) {
     GS_REQUIRE(n >= 0 && num_sorted >= 0 && num_sorted <= n && d >= 0, "bad sizes");
     GS_REQUIRE(num_tiles > 0 && tiles_x > 0, "bad tile grid");
     GS_REQUIRE(tile_ranges != nullptr, "tile_ranges is NULL");
@@ -846,6 +866,8 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     GS_REQUIRE(sorted_ids && offsets && tile_rect && workspace && entry_ids, "NULL array argument");
     GS_REQUIRE(entry_keys == nullptr || depth_keys != nullptr, "entry_keys needs depth_keys");
     GS_REQUIRE(algo >= 0 && algo <= 3, "algo must be 0 (auto), 1 (counting), 2 (radix) or 3 (blocked)");
+    GS_REQUIRE(list_cap <= 0 || algo == GS_BIN_COUNTING || (algo == GS_BIN_AUTO && num_tiles <= kMaxCountingTiles),
+               "truncated lists (list_cap) need the flat counting sort");
     const bool counting = algo == GS_BIN_COUNTING || (algo == GS_BIN_AUTO && num_tiles <= kMaxCountingTiles);
     GS_REQUIRE(counters_dev == nullptr || counting || algo == GS_BIN_BLOCKED, "device-side sizes (counters_dev) need a counting sort");
     if (algo == GS_BIN_BLOCKED) {
@@ -937,7 +959,8 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
             const int64_t warps = (num_sorted + 31) / 32;
             scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
                 sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, local_pos, base16,
-                super_tab, tile_start, depth_keys, entry_ids, entry_keys);
+                super_tab, tile_start, depth_keys, entry_ids, entry_keys,
+                ListCap{list_cap > 0 ? (uint32_t)list_cap : 0xFFFFFFFFu, nullptr, nullptr});
         }
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(5);
@@ -973,5 +996,32 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
     }
+    return GS_OK;
+}
+
+extern "C" int gs_bin_complete(int64_t n, int64_t num_sorted, int64_t d, const int32_t* sorted_ids, const int64_t* offsets,
+                               const uint16_t* tile_rect, int32_t tiles_x, int32_t num_tiles, const void* workspace,
+                               int64_t workspace_bytes, int32_t list_cap, const uint8_t* tile_flags,
+                               const int32_t* flag_count, int32_t* entry_ids, const int64_t* counters_dev, void* stream) {
+    GS_REQUIRE(n >= 0 && num_sorted >= 0 && num_sorted <= n && d >= 0, "bad sizes");
+    GS_REQUIRE(num_tiles > 0 && tiles_x > 0 && num_tiles <= kMaxCountingTiles, "bad tile grid");
+    GS_REQUIRE(list_cap > 0 && tile_flags && flag_count, "gs_bin_complete needs the list_cap of the first pass, tile_flags and flag_count");
+    if (d == 0 || num_sorted == 0) return GS_OK;
+    GS_REQUIRE(sorted_ids && offsets && tile_rect && workspace && entry_ids, "NULL array argument");
+    DeviceGuard guard(entry_ids);
+    const CountLayout C = count_layout(num_sorted, d, num_tiles);
+    if (workspace_bytes < C.total) {
+        set_error("gs_bin_complete: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)C.total);
+        return GS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    const char* wsc = (const char*)workspace;
+    const BinSizes sizes = {num_sorted, d, counters_dev};
+    const int64_t warps = (num_sorted + 31) / 32;
+    scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, (const uint8_t*)(wsc + C.local_pos),
+        (const uint16_t*)(wsc + C.base16), (const uint32_t*)(wsc + C.super_tab), (const uint32_t*)(wsc + C.tile_start), nullptr,
+        entry_ids, nullptr, ListCap{(uint32_t)list_cap, tile_flags, flag_count});
+    GS_CUDA_TRY(cudaGetLastError());
+    count_launches(1);
     return GS_OK;
 }

@@ -234,12 +234,15 @@ __global__ void __launch_bounds__(32, GS_FWD_MINB)
 raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, int any_visible_host, const int64_t* __restrict__ counters_dev,
-                  const int32_t* __restrict__ tile_order, float* __restrict__ image, float* __restrict__ alpha, float* __restrict__ depth,
-                  float4* __restrict__ pix_state, int32_t* __restrict__ n_consumed,
+                  const int32_t* __restrict__ tile_order, int list_cap, uint8_t* __restrict__ tile_flags,
+                  int32_t* __restrict__ flag_count, int rerun, float* __restrict__ image, float* __restrict__ alpha,
+                  float* __restrict__ depth, float4* __restrict__ pix_state, int32_t* __restrict__ n_consumed,
                   int32_t* __restrict__ tile_consumed) {
     __shared__ float4 srec[GS_PREFETCH ? 2 : 1][kBatch * 3];
 
     const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;      // any permutation of the tiles
+    // truncated lists: the re-run pass touches only the tiles the first pass flagged (usually none)
+    if (rerun && (*flag_count == 0 || tile_flags[tile] == 0)) return;
     const int lane = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int py = ty * kTile + (lane >> 1);
@@ -261,7 +264,9 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         ncons[2 * p] = ncons[2 * p + 1] = -1;
     }
 
-    const int2 range = tile_ranges[tile];
+    int2 range = tile_ranges[tile];
+    const int full_end = range.y;
+    if (list_cap > 0 && !rerun) range.y = min(range.y, range.x + list_cap);      // the stored prefix of this tile's list
     int walked = 0;
 #if GS_PREFETCH
     int buf = 0;
@@ -304,6 +309,16 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                                                : fwd_batch<false, kTrack>(srec[0], cnt, base - range.x, fpy, fpx, A, Cr, Cg, Cb, Ds, ncons));
     }
 #endif
+
+    if (range.y < full_end) {                       // stopped at the end of the stored prefix: did the tile need more?
+        bool alive = false;
+#pragma unroll
+        for (int p = 0; p < kPairs; ++p) alive |= (A[p].x < kTermA) | (A[p].y < kTermA);
+        if (__any_sync(0xffffffffu, alive) && lane == 0) {
+            tile_flags[tile] = 1;
+            atomicAdd(flag_count, 1);
+        }
+    }
 
     // epilogue: renderer.py:359-367 (or :74-83 when nothing passed culling)
     const int64_t plane = (int64_t)img_w * img_h;
@@ -707,23 +722,28 @@ static int check_raster_args(int32_t img_w, int32_t img_h, int32_t tile_size, co
 
 extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, const int32_t* entry_ids,
                              const int32_t* tile_ranges, const float* splat_rec, const float* bg,
-                             int32_t any_visible_host, const int64_t* counters_dev, const int32_t* tile_order, float* image,
+                             int32_t any_visible_host, const int64_t* counters_dev, const int32_t* tile_order,
+                             int32_t list_cap, uint8_t* tile_flags, int32_t* flag_count, int32_t rerun, float* image,
                              float* alpha, float* depth, float* pix_state, int32_t* n_consumed, int32_t* tile_consumed,
                              void* stream) {
     const int rc = check_raster_args(img_w, img_h, tile_size, "gs_raster_fwd");
     if (rc != GS_OK) return rc;
     GS_REQUIRE(tile_ranges && bg && image && alpha && depth && pix_state && tile_consumed, "NULL array argument");
+    GS_REQUIRE((list_cap <= 0 && !rerun) || (tile_flags && flag_count), "truncated lists need tile_flags and flag_count");
+    if (list_cap <= 0) list_cap = 0;
     DeviceGuard guard(image);
     const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_consumed) {
         raster_fwd_kernel<true><<<tiles_x * tiles_y, 32, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            counters_dev, tile_order, image, alpha, depth, (float4*)pix_state, n_consumed, tile_consumed);
+            counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
+            n_consumed, tile_consumed);
     } else {
         raster_fwd_kernel<false><<<tiles_x * tiles_y, 32, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            counters_dev, tile_order, image, alpha, depth, (float4*)pix_state, nullptr, tile_consumed);
+            counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
+            nullptr, tile_consumed);
     }
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);

@@ -262,21 +262,41 @@ class _RasterizeFn(torch.autograd.Function):
         if prev is not None:
             check(lib.gs_tile_order(tiles, ptr(prev), None, ptr(bins.tile_order), stream), "gs_tile_order")
 
+        # truncated lists (flat counting sort, not in debug mode): store and composite only each tile's first
+        # `cap` list entries; a tile that needs more is flagged, completed and composited again by the two
+        # self-skipping completion launches, so the result never depends on `cap`
+        cap = int(bins.list_cap or 0) if (bins.algo in (0, 1) and not track) else 0
+        flag_bytes = (tiles + 3) // 4 * 4
+        flagbuf = torch.zeros(flag_bytes + 4, dtype=_U8, device=dev) if cap else None
+        tile_flags = flagbuf[:tiles] if cap else None
+        flag_count = flagbuf[flag_bytes:].view(_I32) if cap else None
+
         def enqueue(num_sorted, d_size, counters_dev):
             entry_ids = torch.empty(max(d_size, 1), dtype=_I32, device=dev)
             ws_bytes = int(lib.gs_bin_workspace_bytes(num_sorted, d_size, tiles))
             ws = torch.empty(ws_bytes, dtype=_U8, device=dev)
+            if cap:
+                flagbuf.zero_()
             with _timed("bin_sort", dev):
                 check(lib.gs_bin_sort(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
                                       ptr(bins.depth_keys), tiles_x, tiles, int(bins.algo), ptr(ws), ws.numel(),
-                                      ptr(entry_ids), ptr(tile_ranges), None, counters_dev, stream), "gs_bin_sort")
+                                      ptr(entry_ids), ptr(tile_ranges), None, counters_dev, cap, stream), "gs_bin_sort")
             if prev is None:                      # this frame's list lengths, available as soon as the binning has run
                 check(lib.gs_tile_order(tiles, None, ptr(tile_ranges), ptr(bins.tile_order), stream), "gs_tile_order")
-            with _timed("raster_fwd", dev):
-                check(lib.gs_raster_fwd(W, H, T, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg),
-                                        int(bins.num_vis > 0) if counters_dev is None else 0, counters_dev, ptr(bins.tile_order),
+            vis_host = int(bins.num_vis > 0) if counters_dev is None else 0
+
+            def composite(rerun):
+                check(lib.gs_raster_fwd(W, H, T, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), vis_host, counters_dev,
+                                        ptr(bins.tile_order), cap, ptr(tile_flags), ptr(flag_count), rerun,
                                         ptr(image), ptr(alpha), ptr(depth), ptr(pix_state),
                                         ptr(n_consumed), ptr(tile_consumed), stream), "gs_raster_fwd")
+            with _timed("raster_fwd", dev):
+                composite(0)
+                if cap:
+                    check(lib.gs_bin_complete(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
+                                              tiles_x, tiles, ptr(ws), ws.numel(), cap, ptr(tile_flags), ptr(flag_count),
+                                              ptr(entry_ids), counters_dev, stream), "gs_bin_complete")
+                    composite(1)
             return entry_ids
 
         entry_ids = None
@@ -290,6 +310,8 @@ class _RasterizeFn(torch.autograd.Function):
         if entry_ids is None:
             entry_ids = enqueue(bins.num_sorted, bins.D, None)
         entry_ids = entry_ids[:bins.D]
+        if cap:
+            bins.report_flagged(flag_count)         # asynchronous: the next frame doubles the cap if tiles were flagged
         bins.entry_ids, bins.tile_ranges = entry_ids, tile_ranges
         bins.renderer_consumed[(dev.index, W, H)] = tile_consumed
 
@@ -351,8 +373,25 @@ class _FrameBins:
         self.prev_consumed = None
         self.tile_order = None
         self.fwd_order = renderer.fwd_tile_order
+        self._renderer = renderer
+        fb = renderer._cap_feedback.get(device.index)
+        if fb is not None and fb[1].query():          # the previous frame's flagged-tile count has arrived
+            if int(fb[0][0]) > 0 and renderer.list_cap:
+                renderer.list_cap = min(int(renderer.list_cap) * 2, 1 << 30)
+            renderer._cap_feedback[device.index] = None
+        self.list_cap = renderer.list_cap
         self.num_sorted = self.D = self.num_vis = None
         self.entry_ids = self.tile_ranges = None
+
+    def report_flagged(self, flag_count):
+        slot = self._renderer._cap_pinned.get(self.device.index)
+        if slot is None:
+            slot = self._renderer._cap_pinned[self.device.index] = torch.zeros(1, dtype=_I32).pin_memory()
+        if self._renderer._cap_feedback.get(self.device.index) is None:      # one report in flight at a time
+            slot.copy_(flag_count, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._renderer._cap_feedback[self.device.index] = (slot, ev)
 
     def start_readback(self):
         self._host.copy_(self.counters, non_blocking=True)
@@ -412,6 +451,11 @@ class GaussianRenderer:
         # work estimate behind the forward's tile launch order: "ranges" = this frame's list lengths,
         # "previous" = what the tiles consumed in the previous frame of the same size (falls back to "ranges")
         self.fwd_tile_order = "ranges"
+        # truncated tile lists: entries stored / composited per tile before the completion path kicks in (0 = complete
+        # lists).  Doubled automatically when a frame had to complete tiles.
+        self.list_cap = 1024
+        self._cap_feedback: Dict[int, Optional[tuple]] = {}
+        self._cap_pinned: Dict[int, torch.Tensor] = {}
         _lib.load()   # fail at construction, not at first render, if the extension is missing
 
     def accumulate_into(self, sink):

@@ -273,7 +273,7 @@ def test_sort_keys_bit_exact_vs_oracle():
     for algo in (1, 2, 3):       # flat counting sort, library radix sort, blocked counting sort: identical sequences
         entry_ids.fill_(-1); ekeys.fill_(-1)
         _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
-                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, st), "sort")
+                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, 0, st), "sort")
         assert torch.equal(ekeys.cpu(), o["sort_keys"]), algo
         assert torch.equal(entry_ids.cpu().long(), o["sort_ids"]), algo
         util.assert_same_ranges(ranges, o["tile_ranges"])
@@ -716,3 +716,45 @@ def test_rectangles_of_more_than_64_tiles():
     util.assert_images_close(c, o, rd._last_debug["n_consumed"], o["n_consumed"], "big rectangles")
     assert util.rel_err(gg.get_xyz.grad, leaf["xyz"].grad) < GRAD_TOL
     assert util.rel_err(gg.get_opacity.grad, leaf["op"].grad) < GRAD_TOL
+
+
+# ----------------------------------------------------------------------------------------------
+# (8) truncated tile lists: only each tile's first `list_cap` entries are stored / composited; tiles that need
+#     more are flagged, completed and composited again -- the result must not depend on the cap
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cap", [8, 40, 100000])
+def test_truncated_lists_give_the_same_frame_as_complete_lists(cap):
+    import gsplat_b200 as gb
+    s = so.scene_aniso(5000, 123)
+    s["scaling"] = s["scaling"] + math.log(2.0)
+    s["opacity"] = s["opacity"] - 1.0                       # transparent enough that tiles walk > 100 entries
+    m = util.cuda_model_from_params(s)
+    cam = gb.Camera.orbit(2, 7, 240, 160)
+    st = gb.RenderSettings(160, 240, torch.tensor([0.05, 0.1, 0.2]))
+    w = tuple(t.cuda() for t in so.loss_weights(160, 240))
+
+    def frame(rd):
+        for p in (m._xyz, m._scaling, m._rotation, m._opacity, m._features_dc, m._features_rest):
+            p.grad = None
+        out = rd.render(cam, m, st)
+        so.weighted_loss(out, w).backward()
+        return out, rd._last_debug["tile_consumed"].clone(), m._xyz.grad.clone(), m._opacity.grad.clone()
+
+    full = gb.GaussianRenderer()
+    full.list_cap = 0
+    ref = frame(full)
+    assert int(ref[1].max()) > 100                          # the scene does need more than the small caps
+    rd = gb.GaussianRenderer()
+    rd.list_cap = cap
+    for it in range(2):                                     # exact path, then the optimistic path
+        got = frame(rd)
+        for k in ("image", "alpha", "depth"):
+            assert torch.equal(got[0][k], ref[0][k]), (cap, it, k)
+        assert torch.equal(got[1], ref[1])
+        assert util.rel_err(got[2], ref[2]) < 1e-5 and util.rel_err(got[3], ref[3]) < 1e-5
+    torch.cuda.synchronize()
+    rd.render(cam, m, st)                                   # a later frame has seen the report of flagged tiles
+    if cap < 100:
+        assert rd.list_cap > cap                            # the cap grew because tiles had to be completed
+    else:
+        assert rd.list_cap == cap
