@@ -1,0 +1,70 @@
+"""CPU: host-side logic around the render path -- flat gradient buffer layout, view sharding, and the bench.py
+reference arm's output contract (one JSON line on stdout)."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+import gsplat_b200 as gb
+from tests.conftest import ROOT
+
+mv = gb.multiview
+
+
+def test_flat_grad_buffer_layout_is_16_byte_aligned_for_any_n():
+    for n in (1, 5, 1001, 4096):
+        m = gb.GaussianModel(device="cpu")
+        m.create_from_random(n, seed=0)
+        buf = mv.FlatGradBuffer(m)
+        assert buf.peer is None                                     # no process group: plain tensor, NCCL/gloo path
+        base = buf.storage.data_ptr()
+        for v, name in zip(buf.views, mv.PARAM_ORDER):
+            assert (v.data_ptr() - base) % 16 == 0, (n, name)
+            assert v.shape == getattr(m, name).shape
+        for t in (buf.grad_norm_sum, buf.vis_count, buf.max_radii):
+            assert (t.data_ptr() - base) % 16 == 0 and t.shape == (n,)
+        assert buf.sum_elems % 4 == 0 and buf.max_elems % 4 == 0
+        assert buf.storage.numel() == buf.sum_elems + buf.max_elems
+        # the views tile the storage without overlap
+        spans = sorted((v.data_ptr() - base, v.numel() * 4) for v in buf.views + [buf.grad_norm_sum, buf.vis_count, buf.max_radii])
+        for (a, la), (b, _) in zip(spans, spans[1:]):
+            assert a + la <= b
+
+
+def test_install_zeroes_unless_the_first_view_will_overwrite():
+    m = gb.GaussianModel(device="cpu")
+    m.create_from_random(10, seed=0)
+    buf = mv.FlatGradBuffer(m)
+    buf.storage.fill_(3.0)
+    buf.install()
+    assert float(buf.storage.abs().max()) == 0.0 and buf.fresh is False
+    assert m._xyz.grad.data_ptr() == buf.views[0].data_ptr() and m._features_rest.grad is None
+    buf.storage.fill_(3.0)
+    buf.install(zero=False)
+    assert float(buf.storage.min()) == 3.0 and buf.fresh is True
+
+
+def test_shard_views_partitions_every_view_exactly_once():
+    for views in (0, 1, 7, 8, 64):
+        for world in (1, 2, 3, 8):
+            parts = [mv.shard_views(views, r, world) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(views))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            assert all(p == list(range(p[0], p[0] + len(p))) for p in parts if p)     # contiguous blocks
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-tiles", "2"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["metric"] == "fwd+bwd frames/s at 1080p, 1M Gaussians" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("config[1]")
