@@ -127,3 +127,23 @@ def test_bin_tiles_equals_append_loop():
     for t in range(tiles_x * tiles_y):
         assert flat[int(ranges[t, 0]):int(ranges[t, 1])].tolist() == lists[t]
     assert bool((keys[1:] >= keys[:-1]).all())
+
+
+def test_sh_basis_of_the_oracle_is_orthonormal_on_the_sphere():
+    """The SH extension is unpinned by the reference (its evaluator is a stub), so the oracle's basis is checked
+    against the definition instead: Y_1..Y_15 (with Y_0 = 1/(2 sqrt(pi))) are orthonormal under the sphere integral."""
+    import numpy as np
+    import torch
+    from oracle import splat_oracle as so
+    nodes, weights = np.polynomial.legendre.leggauss(24)          # cos(theta) quadrature, exact for degree <= 47
+    phis = (np.arange(48) + 0.5) * (2 * np.pi / 48)               # uniform phi: exact for trigonometric degree < 48
+    ct, ph = np.meshgrid(nodes, phis, indexing="ij")
+    st = np.sqrt(1 - ct ** 2)
+    d = torch.tensor(np.stack([st * np.cos(ph), st * np.sin(ph), ct], axis=-1).reshape(-1, 3), dtype=torch.float64)
+    w = torch.tensor((weights[:, None] * np.full_like(ph, 2 * np.pi / 48)).reshape(-1), dtype=torch.float64)
+    Y = so.sh_basis(3, d)                                          # [Q, 15]
+    Y = torch.cat([torch.full((Y.shape[0], 1), 0.28209479177387814, dtype=torch.float64), Y], dim=1)
+    gram = (Y * w[:, None]).T @ Y
+    assert torch.allclose(gram, torch.eye(16, dtype=torch.float64), atol=1e-9)
+    for deg, terms in ((1, 3), (2, 8)):                            # lower degrees are prefixes of the same basis
+        assert torch.equal(so.sh_basis(deg, d), so.sh_basis(3, d)[:, :terms])
