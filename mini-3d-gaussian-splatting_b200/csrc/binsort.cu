@@ -157,7 +157,10 @@ struct ListCap {
     uint32_t limit;                 // first pass: store entries with in-tile index < limit
     const uint8_t* tile_flags;      // completion pass: tiles to complete
     const int32_t* flag_count;      // completion pass: number of flagged tiles (NULL in the first pass)
+    const int32_t* close_chunk;     // first pass (optional): per 8x8-tile block, the first chunk from which every tile of
+    int blocks_x;                   //   the block already holds `limit` entries -- later ranks skip the block entirely
 };
+constexpr int kCloseBlk = 8;
 __device__ __forceinline__ bool resolve_sizes(const BinSizes& z, int64_t& num_sorted) {
     num_sorted = z.num_sorted;
     if (z.dev != nullptr) {
@@ -378,6 +381,29 @@ tile_scan_kernel(BinSizes sizes, int num_tiles, const uint32_t* __restrict__ til
     }
 }
 
+// 3c. truncated lists: from which chunk on is a tile's stored prefix full?  before(c, t) = super_tab + base16 is
+// non-decreasing in the chunk index c, so one binary search per tile finds the first chunk with before >= limit
+// (num_chunks if the tile's list is shorter than the limit); the maximum over the tiles of an 8x8 block is the chunk
+// from which the whole block is closed.  Depth ranks are sorted, so on config[1] ~60 % of the ranks meet closed
+// blocks only and the scatter drops them after reading their rectangle.
+__global__ void __launch_bounds__(256)
+close_chunk_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, const uint16_t* __restrict__ base16,
+                   const uint32_t* __restrict__ super_tab, uint32_t limit, int blocks_x, int32_t* __restrict__ close_chunk) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    int64_t num_sorted;
+    if (!resolve_sizes(sizes, num_sorted)) return;
+    const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
+    int lo = 0, hi = num_chunks;                      // first c in [0, num_chunks] with before(c, t) >= limit
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t before = super_tab[(int64_t)(mid / kSuper) * row_tiles + t] + (uint32_t)base16[(int64_t)mid * row_tiles + t];
+        if (before >= limit) hi = mid; else lo = mid + 1;
+    }
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    atomicMax(&close_chunk[(ty / kCloseBlk) * blocks_x + tx / kCloseBlk], lo);
+}
+
 // 4. parallel scatter in rank order.  One warp per 32 consecutive ranks; for each rank the lanes serve
 // its tiles side by side, so the table reads of a rectangle row and the local_pos read are coalesced.
 // Measured floor: the 26 M four-byte stores land in 26 M different 32-byte sectors and the kernel runs
@@ -404,12 +430,23 @@ scatter_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int
     if (j < num_sorted) {
         id = sorted_ids[j];
         off = offsets[j];
-        d = make_desc(tile_rect[id], tiles_x, cnt);
+        const ushort4 r = tile_rect[id];
+        d = make_desc(r, tiles_x, cnt);
         if (entry_keys) dk = depth_keys[id];
+        if (cap.close_chunk != nullptr && cap.flag_count == nullptr) {
+            // every block this rectangle meets is already closed at this rank's chunk: nothing of it will be stored
+            const int c = (int)(j / kChunk);
+            bool open = false;
+            for (int by = r.y / kCloseBlk; by <= (int)r.w / kCloseBlk; ++by)
+                for (int bx = r.x / kCloseBlk; bx <= (int)r.z / kCloseBlk; ++bx) open |= c < cap.close_chunk[by * cap.blocks_x + bx];
+            if (!open) cnt = 0;
+        }
     }
-    const int limit = (int)min((int64_t)32, num_sorted - j0);
-#pragma unroll 4
-    for (int l = 0; l < limit; ++l) {
+    // only the ranks that still have something to store are visited
+    unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+    while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
         const int s_id = __shfl_sync(0xffffffffu, id, l);
         const long long s_off = __shfl_sync(0xffffffffu, off, l);
         const int s_origin = __shfl_sync(0xffffffffu, d.origin, l);
@@ -446,7 +483,7 @@ scatter_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int
 }
 
 struct CountLayout {
-    int64_t counts, base16, super_tab, tile_total, tile_start, local_pos, total;
+    int64_t counts, base16, super_tab, tile_total, tile_start, local_pos, close_chunk, total;
     int num_chunks, num_supers, row_tiles;
 };
 static CountLayout count_layout(int64_t num_sorted_cap, int64_t d, int32_t num_tiles) {
@@ -462,6 +499,7 @@ static CountLayout count_layout(int64_t num_sorted_cap, int64_t d, int32_t num_t
     L.tile_total = o; o += align_up((int64_t)L.row_tiles * 4, 256);
     L.tile_start = o; o += align_up((int64_t)L.row_tiles * 4, 256);
     L.local_pos = o;  o += align_up(d, 256);
+    L.close_chunk = o; o += align_up(((int64_t)num_tiles / kCloseBlk + 2) * 4, 256);     // >= blocks of any grid shape
     L.total = o;
     return L;
 }
@@ -956,11 +994,23 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
         tile_scan_kernel<<<1, 1024, 0, st>>>(sizes, num_tiles, tile_total, tile_start, tile_ranges);
         GS_CUDA_TRY(cudaGetLastError());
         {
+            ListCap cap = {list_cap > 0 ? (uint32_t)list_cap : 0xFFFFFFFFu, nullptr, nullptr, nullptr, 0};
+            if (list_cap > 0 && num_tiles % tiles_x == 0) {
+                const int tiles_y = num_tiles / tiles_x;
+                const int blocks_x = (tiles_x + kCloseBlk - 1) / kCloseBlk, blocks_y = (tiles_y + kCloseBlk - 1) / kCloseBlk;
+                int32_t* close_chunk = (int32_t*)(wsc + C.close_chunk);
+                GS_CUDA_TRY(cudaMemsetAsync(close_chunk, 0, (size_t)blocks_x * blocks_y * sizeof(int32_t), st));
+                close_chunk_kernel<<<(num_tiles + 255) / 256, 256, 0, st>>>(sizes, num_tiles, tiles_x, C.row_tiles, base16,
+                                                                            super_tab, cap.limit, blocks_x, close_chunk);
+                GS_CUDA_TRY(cudaGetLastError());
+                count_launches(1);
+                cap.close_chunk = close_chunk;
+                cap.blocks_x = blocks_x;
+            }
             const int64_t warps = (num_sorted + 31) / 32;
             scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
                 sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, local_pos, base16,
-                super_tab, tile_start, depth_keys, entry_ids, entry_keys,
-                ListCap{list_cap > 0 ? (uint32_t)list_cap : 0xFFFFFFFFu, nullptr, nullptr});
+                super_tab, tile_start, depth_keys, entry_ids, entry_keys, cap);
         }
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(5);
@@ -1020,7 +1070,7 @@ extern "C" int gs_bin_complete(int64_t n, int64_t num_sorted, int64_t d, const i
     scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, (const uint8_t*)(wsc + C.local_pos),
         (const uint16_t*)(wsc + C.base16), (const uint32_t*)(wsc + C.super_tab), (const uint32_t*)(wsc + C.tile_start), nullptr,
-        entry_ids, nullptr, ListCap{(uint32_t)list_cap, tile_flags, flag_count});
+        entry_ids, nullptr, ListCap{(uint32_t)list_cap, tile_flags, flag_count, nullptr, 0});
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
     return GS_OK;
