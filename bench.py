@@ -428,6 +428,9 @@ def main():
             "config": {"workload": WORKLOAD, "views_per_gpu_per_step": 1, "splats": n, "resolution": [WIDTH, HEIGHT],
                        "visible": V, "tile_pairs_D": D, "consumed_entries_E": E,
                        "l2": "flushed before every timed step (256 MiB memset); per-step working set > L2",
+                       "renderer": {"binning": "flat counting sort, optimistic sizes, tile lists truncated to their first "
+                                               f"{rd.list_cap} entries with a completion path (result identical to complete lists)",
+                                    "tile_order": f"longest first (forward: {rd.fwd_tile_order}; backward: exact work)"},
                        "parallelism": (f"view-sharded dp{world}, replicated Gaussians, gradient/statistics exchange of 17N floats: "
                                        + ("one peer-memory kernel per rank over NVLink (gs_peer_allreduce)" if buf.peer is not None
                                           else f"NCCL all_reduce (peer path unavailable: {buf.peer_error})")) if world > 1 else "single GPU"},
