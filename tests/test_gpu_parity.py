@@ -405,6 +405,36 @@ def test_full_size_image_properties(full_scene):
           f"saturated pixels {float((a >= 0.995).float().mean()):.4f}")
 
 
+def test_full_size_truncated_lists_and_closed_blocks_equal_complete_lists(full_scene):
+    """BASELINE config[1] through the default renderer settings (tile lists truncated to 1 024 entries, closed-block
+    skipping, optimistic sizes on the second frame) against complete lists: identical frame, identical walk lengths."""
+    import gsplat_b200 as gb
+    m, rd_debug, out_debug, W, H = full_scene
+    cam = gb.Camera.look_at_origin_c0(W, H)
+    st = gb.RenderSettings(H, W, torch.zeros(3))
+    full = gb.GaussianRenderer()
+    full.list_cap = 0
+    with torch.no_grad():
+        ref = full.render(cam, m, st)
+        tc_ref = full._last_debug["tile_consumed"].clone()
+        rd = gb.GaussianRenderer()
+        assert rd.list_cap == 1024
+        for it in range(2):                                  # exact sizes, then optimistic sizes
+            got = rd.render(cam, m, st)
+            for k in ("image", "alpha", "depth"):
+                assert torch.equal(got[k], ref[k]), (it, k)
+            assert torch.equal(rd._last_debug["tile_consumed"], tc_ref)
+            # the stored prefix of every tile's list is the prefix of the complete list
+            rng = rd._last_debug["tile_ranges"].long()
+            assert torch.equal(rng, full._last_debug["tile_ranges"].long())
+            t = int(torch.argmax(rng[:, 1] - rng[:, 0]))
+            b = int(rng[t, 0])
+            assert int(rng[t, 1]) - b > 1024
+            assert torch.equal(rd._last_debug["entry_ids"][b:b + 1024], full._last_debug["entry_ids"][b:b + 1024])
+    for k in ("image", "alpha", "depth"):
+        assert torch.equal(out_debug[k].detach(), ref[k]), k        # and the debug (tracking) kernel variant agrees
+
+
 def test_full_size_sampled_tiles_vs_oracle_forward_and_backward(full_scene):
     """Tiles sampled across the 1080p frame: forward values and, with the loss restricted to those
     tiles, every parameter gradient against oracle autograd."""
