@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 13
+#define GS_ABI_VERSION 14
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -289,10 +289,13 @@ int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, in
  *   split: |grad[i]| > grad_threshold and mean sigma > large_sigma -> replaced by two children at
  *          xyz -+ R[:,0]*0.5*mean sigma, sigma*0.75, opacity logit clamped to [-6,6];
  *   prune: rows with sigmoid(opacity) <= min_opacity are dropped.
- * gs_densify_plan classifies and scans; counts (device, 4 x int64) = {surviving originals, clone copies,
- * split parents, total rows}.  The caller reads the counts, allocates the six output arrays with `total`
- * rows and calls gs_densify_apply with the same workspace.  Output order: surviving originals, clone
+ * gs_densify_plan classifies and scans; counts (device, 5 x int64) = {surviving originals, clone copies,
+ * split parents, total rows, clone candidates}.  The caller reads the counts, allocates the six output arrays with
+ * `total` rows and calls gs_densify_apply with the same workspace.  Output order: surviving originals, clone
  * copies, "minus" children, "plus" children -- each in index order (what the sequential formulation yields).
+ * noise [clone candidates, 3]: row j is the jitter of the j-th splat (in index order) that met the clone
+ * criterion -- whether or not its copy survives the opacity test -- i.e. the randn(k, 3) block that
+ * gaussian_model.py:171 draws, so the same generator yields the same clones as the sequential formulation.
  * ------------------------------------------------------------------------------------- */
 int64_t gs_densify_workspace_bytes(int64_t n);
 

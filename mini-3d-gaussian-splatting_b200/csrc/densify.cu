@@ -17,10 +17,12 @@ namespace gs {
 
 struct Tri {
     int a, b, c;       // kept originals, clone copies, split parents (that survive the opacity test)
+    int d;             // clone CANDIDATES (before the opacity test): the rank in this channel indexes the jitter noise,
+                       // which the sequential formulation draws as randn(k, 3) for all k candidates
 };
 struct TriSum {
     __host__ __device__ __forceinline__ Tri operator()(const Tri& x, const Tri& y) const {
-        return Tri{x.a + y.a, x.b + y.b, x.c + y.c};
+        return Tri{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d};
     }
 };
 
@@ -50,17 +52,20 @@ densify_classify_kernel(int64_t n, const float* __restrict__ scaling_log, const 
     f.a = (!split && keep_self) ? 1 : 0;
     f.b = (clone && keep_self) ? 1 : 0;
     f.c = (split && keep_child) ? 1 : 0;
+    f.d = clone ? 1 : 0;
     flags[i] = f;
 }
 
 __global__ void densify_totals_kernel(int64_t n, const Tri* __restrict__ flags, const Tri* __restrict__ pos, int64_t* counts) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        Tri t = {0, 0, 0};
-        if (n > 0) t = Tri{pos[n - 1].a + flags[n - 1].a, pos[n - 1].b + flags[n - 1].b, pos[n - 1].c + flags[n - 1].c};
+        Tri t = {0, 0, 0, 0};
+        if (n > 0) t = Tri{pos[n - 1].a + flags[n - 1].a, pos[n - 1].b + flags[n - 1].b, pos[n - 1].c + flags[n - 1].c,
+                           pos[n - 1].d + flags[n - 1].d};
         counts[0] = t.a;
         counts[1] = t.b;
         counts[2] = t.c;
         counts[3] = (int64_t)t.a + t.b + 2 * (int64_t)t.c;
+        counts[4] = t.d;
     }
 }
 
@@ -92,7 +97,7 @@ densify_apply_kernel(int64_t n, const Tri* __restrict__ flags, const Tri* __rest
     if (f.b) {                                      // clone copy: jittered position, everything else equal
         const int64_t d = kept + p.b;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) m.o_xyz[d * 3 + k] = m.xyz[i * 3 + k] + noise[i * 3 + k] * half_mean;
+        for (int k = 0; k < 3; ++k) m.o_xyz[d * 3 + k] = m.xyz[i * 3 + k] + noise[(int64_t)p.d * 3 + k] * half_mean;
         copy_row(m.dc, m.o_dc, i, d, 3); copy_row(m.rest, m.o_rest, i, d, 45);
         copy_row(m.scaling, m.o_scaling, i, d, 3); copy_row(m.rotation, m.o_rotation, i, d, 4);
         m.o_opacity[d] = m.opacity[i];
@@ -130,7 +135,7 @@ struct DensifyLayout {
 static DensifyLayout densify_layout(int64_t n) {
     DensifyLayout L;
     size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveScan(nullptr, scan_bytes, (const Tri*)nullptr, (Tri*)nullptr, TriSum(), Tri{0, 0, 0}, n);
+    cub::DeviceScan::ExclusiveScan(nullptr, scan_bytes, (const Tri*)nullptr, (Tri*)nullptr, TriSum(), Tri{0, 0, 0, 0}, n);
     int64_t o = 0;
     L.flags = o; o += align256(n * (int64_t)sizeof(Tri));
     L.pos = o;   o += align256(n * (int64_t)sizeof(Tri));
@@ -158,7 +163,7 @@ extern "C" int gs_densify_plan(int64_t n, const float* scaling_log, const float*
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(counts);
     if (n == 0) {
-        GS_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), st));
+        GS_CUDA_TRY(cudaMemsetAsync(counts, 0, 5 * sizeof(int64_t), st));
         return GS_OK;
     }
     GS_REQUIRE(n < (1ll << 30), "n too large");
@@ -175,7 +180,7 @@ extern "C" int gs_densify_plan(int64_t n, const float* scaling_log, const float*
                                                                         large_sigma, min_opacity, flags);
     GS_CUDA_TRY(cudaGetLastError());
     size_t cub_bytes = (size_t)L.cub_bytes;
-    GS_CUDA_TRY(cub::DeviceScan::ExclusiveScan(w + L.cub_temp, cub_bytes, (const Tri*)flags, pos, TriSum(), Tri{0, 0, 0}, n, st));
+    GS_CUDA_TRY(cub::DeviceScan::ExclusiveScan(w + L.cub_temp, cub_bytes, (const Tri*)flags, pos, TriSum(), Tri{0, 0, 0, 0}, n, st));
     densify_totals_kernel<<<1, 32, 0, st>>>(n, flags, pos, counts);
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(2);

@@ -291,7 +291,9 @@ class GaussianModel(nn.Module):
         """Clone, split and prune in one plan + one apply pass on the device (gs_densify_plan /
         gs_densify_apply): same result, row for row, as density_and_clone -> density_and_split ->
         prune_points(opacity > min_opacity) driven by DensityController, with one host read (the four
-        counts) instead of one per step.  `noise` [N,3] is the clone jitter (drawn here if omitted)."""
+        counts) instead of one per step.  `noise` [k,3] is the jitter of the k splats that meet the clone
+        criterion, in index order; when omitted it is drawn AFTER the plan pass as randn(k, 3) -- the draw
+        density_and_clone makes -- so the same generator places the clones where the sequential path does."""
         import ctypes
         from . import _lib
         lib = _lib.load()
@@ -299,21 +301,24 @@ class GaussianModel(nn.Module):
         dev = self._xyz.device
         if dev.type != "cuda":
             raise RuntimeError("densify_fused runs on CUDA tensors only")
-        if noise is None:
-            noise = torch.randn(n, 3, generator=generator, device=dev if generator is None else generator.device).to(dev)
         f32c = lambda t: t.detach().to(torch.float32).contiguous()  # noqa: E731
-        grad, noise = f32c(grad), f32c(noise)
+        grad = f32c(grad)
         params = [f32c(p.data) for p in (self._xyz, self._features_dc, self._features_rest, self._scaling, self._rotation,
                                           self._opacity)]
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             ws_bytes = int(lib.gs_densify_workspace_bytes(n))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            counts = torch.empty(4, dtype=torch.int64, device=dev)
+            counts = torch.empty(5, dtype=torch.int64, device=dev)
             _lib.check(lib.gs_densify_plan(n, _lib.ptr(params[3]), _lib.ptr(params[5]), _lib.ptr(grad), float(grad_threshold),
                                            float(0.01 * scene_extent), float(0.03 * scene_extent), float(min_opacity),
                                            _lib.ptr(ws), ws_bytes, _lib.ptr(counts), stream), "gs_densify_plan")
-            kept, cloned, split, total = (int(v) for v in counts.tolist())
+            kept, cloned, split, total, candidates = (int(v) for v in counts.tolist())
+            if noise is None:
+                noise = torch.randn(candidates, 3, generator=generator, device=dev if generator is None else generator.device)
+            noise = f32c(noise.to(dev))
+            if noise.shape[0] < candidates:
+                raise ValueError(f"noise has {noise.shape[0]} rows, {candidates} splats meet the clone criterion")
             out = [torch.empty((total,) + tuple(p.shape[1:]), dtype=torch.float32, device=dev) for p in params]
             _lib.check(lib.gs_densify_apply(n, _lib.ptr(ws), kept, cloned, split, *[_lib.ptr(p) for p in params], _lib.ptr(noise),
                                             *[_lib.ptr(o) for o in out], stream), "gs_densify_apply")

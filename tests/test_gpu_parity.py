@@ -477,16 +477,17 @@ def test_full_size_sampled_tiles_vs_oracle_forward_and_backward(full_scene):
         flips_total += rep["flips"]
         for k in worst:
             worst[k] = max(worst[k], rep["worst"][k])
-        loss = loss + (wi[:, y0:y1, x0:x1] * rgb.view(3, hh, ww)).sum() + (wa[0, y0:y1, x0:x1] * al.view(hh, ww)).sum() \
-            + 0.1 * (wd[0, y0:y1, x0:x1] * dp.view(hh, ww)).sum()
-        g_img[:, y0:y1, x0:x1] = wi[:, y0:y1, x0:x1]
-        g_a[:, y0:y1, x0:x1] = wa[:, y0:y1, x0:x1]
-        g_d[:, y0:y1, x0:x1] = 0.1 * wd[:, y0:y1, x0:x1]
+        # a pixel that terminates one entry apart from the oracle is masked out of the loss on both sides,
+        # so the gradient comparison below always runs on identical walks
+        keep = (dbg["n_consumed"][y0:y1, x0:x1].cpu().long() == ncons.view(hh, ww).long()).to(torch.float32)
+        loss = loss + (wi[:, y0:y1, x0:x1] * keep * rgb.view(3, hh, ww)).sum() + (wa[0, y0:y1, x0:x1] * keep * al.view(hh, ww)).sum() \
+            + 0.1 * (wd[0, y0:y1, x0:x1] * keep * dp.view(hh, ww)).sum()
+        g_img[:, y0:y1, x0:x1] = wi[:, y0:y1, x0:x1] * keep
+        g_a[:, y0:y1, x0:x1] = wa[:, y0:y1, x0:x1] * keep
+        g_d[:, y0:y1, x0:x1] = 0.1 * wd[:, y0:y1, x0:x1] * keep
     for k, v in worst.items():
         assert v < IMG_TOL, (k, v)
-    print(f"sampled tiles: worst abs diff {worst}, termination flips {flips_total} of {len(sample) * 256} pixels")
-    if flips_total:
-        pytest.skip("a sampled pixel terminates one splat apart from the oracle; gradient comparison needs identical walks")
+    print(f"sampled tiles: worst abs diff {worst}, termination flips {flips_total} of {len(sample) * 256} pixels (masked)")
     loss.backward()
     # CUDA: same restricted loss through the product path; compare the rasteriser-level gradients
     out["viewspace_points"].retain_grad()
