@@ -58,6 +58,7 @@ class FlatGradBuffer:
         self.max_elems = pad4(n)
         self.peer = None
         self.peer_error = None
+        self.fresh = False
         want_peer = peer if peer is not None else os.environ.get("GSPLAT_B200_PEER", "1") != "0"
         storage = None
         if (want_peer and device.type == "cuda" and dist.is_available() and dist.is_initialized()
@@ -68,6 +69,28 @@ class FlatGradBuffer:
                 self.peer_error = f"{type(e).__name__}: {e}"
                 if peer:
                     raise
+        if storage is not None:
+            # One exchange of the still-zero buffer now, at construction: it goes through torch's private symmetric-memory
+            # API (barrier signature, buffer_ptrs) and our kernel, so an API drift or a launch failure shows up here --
+            # where falling back to NCCL is clean -- and not in the middle of a training step.  All ranks agree on the
+            # outcome with one MIN all-reduce.
+            self.storage = storage
+            ok = 1
+            try:
+                self._peer_exchange()
+                torch.cuda.current_stream(device).synchronize()
+                if float(storage.abs().max()) != 0.0:
+                    raise RuntimeError("probe exchange of a zero buffer returned non-zero values")
+            except Exception as e:                               # noqa: BLE001 -- recorded in peer_error, NCCL takes over
+                ok, self.peer_error = 0, f"{type(e).__name__}: {e}"
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) != 1:
+                if self.peer_error is None:
+                    self.peer_error = "peer exchange probe failed on another rank"
+                if peer:
+                    raise RuntimeError(self.peer_error)
+                self.peer, storage = None, None
         if storage is None:
             storage = torch.zeros(self.sum_elems + self.max_elems, dtype=torch.float32, device=device)
         self.storage = storage
@@ -116,19 +139,26 @@ class FlatGradBuffer:
         self.vis_count += vis_f
         torch.maximum(self.max_radii, radii * vis_f, out=self.max_radii)
 
+    def _peer_exchange(self) -> None:
+        import ctypes
+        from . import _lib
+        h = self.peer["handle"]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.storage.device).cuda_stream)
+        h.barrier(channel=0)                 # every rank's buffer is complete (device-side, on this stream)
+        _lib.check(_lib.load().gs_peer_allreduce(self.peer["ptrs"], self.peer["multicast"], self.peer["world"], self.peer["rank"],
+                                                 0, self.sum_elems, self.sum_elems, self.max_elems, stream),
+                   "gs_peer_allreduce")
+        h.barrier(channel=1)                 # every rank's slice has landed everywhere
+
     def all_reduce(self, group=None) -> None:
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
+        if self.fresh:
+            # the write-mode projection backward that was to overwrite the buffer never ran (loss_fn raised, or no
+            # view took the fused path): what the buffer holds is the previous step's result, not this step's
+            raise RuntimeError("FlatGradBuffer.all_reduce: no backward pass has filled the buffer since install(zero=False)")
         if self.peer is not None:
-            import ctypes
-            from . import _lib
-            h = self.peer["handle"]
-            stream = ctypes.c_void_p(torch.cuda.current_stream(self.storage.device).cuda_stream)
-            h.barrier(channel=0)                 # every rank's buffer is complete (device-side, on this stream)
-            _lib.check(_lib.load().gs_peer_allreduce(self.peer["ptrs"], self.peer["multicast"], self.peer["world"], self.peer["rank"],
-                                                     0, self.sum_elems, self.sum_elems, self.max_elems, stream),
-                       "gs_peer_allreduce")
-            h.barrier(channel=1)                 # every rank's slice has landed everywhere
+            self._peer_exchange()
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
@@ -144,6 +174,9 @@ def multiview_step(model, renderer, cameras: Sequence, settings, loss_fn: Callab
     reference allocates but never fills (gaussian_model.py:29-31).
     """
     buf = buffer if buffer is not None else FlatGradBuffer(model)
+    if hasattr(model, "get_num_points") and buf.n != model.get_num_points():
+        raise ValueError(f"FlatGradBuffer was built for {buf.n} splats but the model now holds {model.get_num_points()} "
+                         "(densification changes the row count): build a new FlatGradBuffer(model)")
     ids = list(view_ids) if view_ids is not None else list(range(len(cameras)))
     losses = []
     # B200 renderer: the projection backward adds gradients and statistics into `buf` itself

@@ -23,6 +23,8 @@ import torch
 from . import _lib
 from ._lib import check, ptr
 
+SUPPORTED_TILE_SIZES = (16,)
+MAX_COUNTING_TILES = 200000       # csrc/binsort.cu kMaxCountingTiles: one byte of shared memory per tile
 _U8 = torch.uint8
 _I32 = torch.int32
 _I64 = torch.int64
@@ -432,7 +434,10 @@ class GaussianRenderer:
         if not 0 <= int(sh_degree) <= 3:
             raise ValueError("sh_degree must be 0..3")
         self.sh_degree = int(sh_degree)
-        self.tile_size = tile_size
+        if int(tile_size) not in SUPPORTED_TILE_SIZES:
+            # the reference takes any tile size (renderer.py:24); the kernels here are specialised per size
+            raise ValueError(f"tile_size must be one of {SUPPORTED_TILE_SIZES}, got {tile_size}")
+        self.tile_size = int(tile_size)
         self.radius_min = radius_min
         self.radius_max = radius_max
         self.device = torch.device("cuda")
@@ -568,10 +573,12 @@ class GaussianRenderer:
         bins.prev_consumed = self._tile_consumed.get((device.index, W, H))
         # 0 = the flat counting sort.  3 (blocked two-level sort, coalesced final stores) is bit-identical and
         # measured no faster (385 vs 376 us at config[1]); it needs rectangles of at most 8 tiles per side
-        algo = self.bin_algo if self.bin_algo else 1
+        algo = self.bin_algo if self.bin_algo else (1 if num_tiles <= MAX_COUNTING_TILES else 2)
         if algo == 3 and self.radius_max > 50.0:
             raise ValueError("bin_algo=3 (blocked) needs radius_max <= 50")
         bins.tile_rect, bins.depth_keys, bins.algo = tile_rect, depth_keys, algo
+        if algo == 2:
+            bins.d_cap = None            # the radix path needs exact sizes (and stores complete lists: list_cap is ignored)
         bins.counters = torch.empty(3, dtype=_I64, device=device)
         bins.sorted_ids = torch.empty(n, dtype=_I32, device=device)
         bins.offsets = torch.empty(n, dtype=_I64, device=device)
@@ -588,7 +595,9 @@ class GaussianRenderer:
         num_sorted, D, num_vis = bins.num_sorted, bins.D, bins.num_vis
         entry_ids, tile_ranges, sorted_ids = bins.entry_ids, bins.tile_ranges, bins.sorted_ids
         # capacity for the next frame's optimistic binning: this frame's pair count plus a quarter
-        self._d_cap[device.index] = int(D * 1.25) + 4096 if self.optimistic_binning else None
+        # (gs_bin_sort addresses pairs with int32: a capacity beyond that falls back to exact sizes)
+        cap_next = int(D * 1.25) + 4096
+        self._d_cap[device.index] = cap_next if (self.optimistic_binning and cap_next < (1 << 31)) else None
 
         self.last_stats = {"num_visible": num_vis, "num_binned": num_sorted, "tile_pairs": D}
         self._last_debug = {"tile_consumed": tile_consumed, "n_consumed": n_consumed, "entry_ids": entry_ids,

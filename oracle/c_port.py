@@ -52,6 +52,19 @@ def num_threads() -> int:
     return int(load().oracle_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the port from now on (a launcher such as torchrun exports OMP_NUM_THREADS=1)."""
+    load().oracle_set_num_threads(c_int(int(n)))
+    return num_threads()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:      # pragma: no cover
+        return os.cpu_count() or 1
+
+
 def project(cam16, W, H, xyz, scaling=None, rotation=None, cov3d=None, opacity=None, opacity_is_logit=True, feat0=None,
             rmin=0.01, rmax=50.0):
     lib = load()

@@ -36,6 +36,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* bench.py --impl reference: use all host cores even when a launcher (torchrun) exported OMP_NUM_THREADS=1 */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 /* cam: Rv[9] Tv[3] fx fy cx cy (16 floats), as include/gsplat_b200.h */

@@ -1,0 +1,43 @@
+"""GPU, >= 2 devices: the peer-memory gradient exchange (mini-3d-gaussian-splatting_b200/multiview.py FlatGradBuffer.all_reduce,
+csrc/peer.cu) against NCCL, launched through torchrun -- worlds 2 / 4 / 8 (specialised kernels) and 3 (generic kernel), ragged
+slice boundaries, plain peer loads/stores and the NVSwitch multicast variant.  SURVEY 8e: no reference counterpart (the
+reference is single-device); the acceptance is "reduced buffer == NCCL all_reduce of the same inputs, bit-identical on all ranks".
+The driver's single-GPU tier skips these; bench.py prints the same checks on the real render gradients (`exchange_check`)
+in every N >= 2 line."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _run(world, n, multicast, port):
+    env = dict(os.environ, GSPLAT_B200_MULTICAST=str(int(multicast)), GSPLAT_B200_PEER="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "peer_worker.py"), str(n)],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("PEER_RESULT ")]
+    assert len(line) == 1, r.stdout[-1500:]
+    return json.loads(line[0][len("PEER_RESULT "):])
+
+
+@pytest.mark.parametrize("multicast", [0, 1])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_peer_exchange_equals_nccl(world, multicast):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
+    n = 100003                                    # sum region 1 600 064 floats = 400 016 float4: not divisible by 3 or 8 -> ragged slices
+    res = _run(world, n, multicast, 29600 + 10 * world + multicast)
+    assert res["world"] == world
+    if multicast and not res["multicast"]:
+        pytest.skip("no NVSwitch multicast address on this box: the multimem variant did not run")
+    for rnd in res["rounds"]:
+        assert rnd["sum_rel_err_vs_nccl"] < 2e-6, res            # fp32 sums in a different order
+        assert rnd["max_region_equals_nccl"], res
+        assert rnd["bitwise_same_on_all_ranks"], res
