@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 14
+#define GS_ABI_VERSION 15
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -296,6 +296,9 @@ int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, in
  * noise [clone candidates, 3]: row j is the jitter of the j-th splat (in index order) that met the clone
  * criterion -- whether or not its copy survives the opacity test -- i.e. the randn(k, 3) block that
  * gaussian_model.py:171 draws, so the same generator yields the same clones as the sequential formulation.
+ * src_row (optional, [total] int32): for every output row the index of the original it continues (surviving originals),
+ * or -1 for rows created by this round (clone copies, split children) -- what an optimiser needs to carry its
+ * per-row state across the round.
  * ------------------------------------------------------------------------------------- */
 int64_t gs_densify_workspace_bytes(int64_t n);
 
@@ -307,7 +310,7 @@ int gs_densify_apply(int64_t n, const void* workspace, int64_t kept, int64_t clo
                      const float* xyz, const float* features_dc, const float* features_rest,
                      const float* scaling_log, const float* rotation, const float* opacity, const float* noise,
                      float* o_xyz, float* o_features_dc, float* o_features_rest, float* o_scaling_log,
-                     float* o_rotation, float* o_opacity, void* stream);
+                     float* o_rotation, float* o_opacity, int32_t* src_row, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,39 +16,11 @@ namespace gs {
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-struct GatherCount {
-    const int32_t* tiles_touched;
-    const int32_t* sorted_ids;
-    __host__ __device__ __forceinline__ int64_t operator()(int64_t j) const {
-        return (int64_t)tiles_touched[sorted_ids[j]];
-    }
-};
-
-__global__ void iota_kernel(int64_t n, int32_t* ids) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ids[i] = (int32_t)i;
-}
-
-__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* a, int64_t n, uint32_t v) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (a[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// counters[0] = splats with >=1 tile, counters[1] = total tile pairs, counters[2] = visible splats
-__global__ void counters_kernel(int64_t n, const uint32_t* sorted_keys, const int32_t* sorted_ids,
-                                const int32_t* tiles_touched, const int64_t* offsets, int64_t* counters) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int64_t v_tiles = lower_bound_u32(sorted_keys, n, 0xFFFFFFFEu);
-        const int64_t v_vis = lower_bound_u32(sorted_keys, n, 0xFFFFFFFFu);
-        counters[0] = v_tiles;
-        counters[1] = n > 0 ? offsets[n - 1] + (int64_t)tiles_touched[sorted_ids[n - 1]] : 0;
-        counters[2] = v_vis;
-    }
-}
+// Stage S lives in depthsort.cu (one cooperative kernel: key range, 8-bit LSD passes over the differing bits only,
+// prefix sum of tiles_touched and the counters fused into the last pass).
+int64_t depth_sort_workspace_bytes(int64_t n);
+int depth_sort_launch(int64_t n, const uint32_t* depth_keys, const int32_t* tiles_touched, void* workspace, int64_t workspace_bytes,
+                      int32_t* sorted_ids, int64_t* offsets, int64_t* counters, cudaStream_t st);
 
 // One warp per 32 consecutive depth ranks; for each rank the warp writes that splat's tile ids
 // side by side (coalesced), in row-major tile order.
@@ -511,28 +483,6 @@ static int tile_bits(int32_t num_tiles) {
     return bits;
 }
 
-struct PrepareLayout {
-    int64_t keys_sorted, ids_iota, cub_temp, cub_bytes, total;
-};
-static PrepareLayout prepare_layout(int64_t n) {
-    PrepareLayout L;
-    size_t sort_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 32);
-    GatherCount op{nullptr, nullptr};
-    cub::TransformInputIterator<int64_t, GatherCount, cub::CountingInputIterator<int64_t>> it(
-        cub::CountingInputIterator<int64_t>(0), op);
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (int64_t*)nullptr, n);
-    int64_t o = 0;
-    L.keys_sorted = o; o += align_up(n * 4, 256);
-    L.ids_iota = o;    o += align_up(n * 4, 256);
-    L.cub_temp = o;
-    L.cub_bytes = align_up((int64_t)(sort_bytes > scan_bytes ? sort_bytes : scan_bytes), 256);
-    o += L.cub_bytes;
-    L.total = o;
-    return L;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Blocked (two-level) stable counting sort: GS_BIN_BLOCKED.
 //
@@ -837,7 +787,7 @@ using namespace gs;
 
 extern "C" int64_t gs_bin_workspace_bytes(int64_t n, int64_t d_capacity, int32_t num_tiles) {
     if (n < 0 || d_capacity < 0 || num_tiles <= 0) return GS_ERR_INVALID_ARGUMENT;
-    const int64_t a = prepare_layout(n > 0 ? n : 1).total;
+    const int64_t a = depth_sort_workspace_bytes(n > 0 ? n : 1);
     const int64_t b = sort_layout(d_capacity > 0 ? d_capacity : 1, num_tiles).total;
     const int64_t c = num_tiles <= kMaxCountingTiles ? count_layout(n > 0 ? n : 1, d_capacity > 0 ? d_capacity : 1, num_tiles).total : 0;
     const int64_t e = blocked_layout(n > 0 ? n : 1, num_tiles, blocks_bound(num_tiles)).total;
@@ -860,31 +810,7 @@ extern "C" int gs_bin_prepare(int64_t n, const uint32_t* depth_keys, const int32
     }
     GS_REQUIRE(n < (1ll << 31), "n must fit int32 ids");
     GS_REQUIRE(depth_keys && tiles_touched && workspace && sorted_ids && offsets, "NULL array argument");
-    const PrepareLayout L = prepare_layout(n);
-    if (workspace_bytes < L.total) {
-        set_error("gs_bin_prepare: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)L.total);
-        return GS_ERR_WORKSPACE_TOO_SMALL;
-    }
-    char* ws = (char*)workspace;
-    uint32_t* keys_sorted = (uint32_t*)(ws + L.keys_sorted);
-    int32_t* ids_iota = (int32_t*)(ws + L.ids_iota);
-    void* cub_temp = ws + L.cub_temp;
-    size_t cub_bytes = (size_t)L.cub_bytes;
-    const int threads = 256;
-    iota_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(n, ids_iota);
-    GS_CUDA_TRY(cudaGetLastError());
-    // LSD radix sort is stable: equal depths keep ascending splat index.
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, depth_keys, keys_sorted, (const int32_t*)ids_iota,
-                                                sorted_ids, n, 0, 32, st));
-    GatherCount op{tiles_touched, sorted_ids};
-    cub::TransformInputIterator<int64_t, GatherCount, cub::CountingInputIterator<int64_t>> it(
-        cub::CountingInputIterator<int64_t>(0), op);
-    cub_bytes = (size_t)L.cub_bytes;
-    GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, it, offsets, n, st));
-    counters_kernel<<<1, 32, 0, st>>>(n, keys_sorted, sorted_ids, tiles_touched, offsets, counters);
-    GS_CUDA_TRY(cudaGetLastError());
-    count_launches(2);   // iota + counters
-    return GS_OK;
+    return depth_sort_launch(n, depth_keys, tiles_touched, workspace, workspace_bytes, sorted_ids, offsets, counters, st);
 }
 
 extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32_t* sorted_ids, const int64_t* offsets,

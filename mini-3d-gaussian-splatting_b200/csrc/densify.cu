@@ -81,7 +81,7 @@ __device__ __forceinline__ void copy_row(const float* __restrict__ src, float* _
 // One thread per original splat writes all the rows it produces (0..2 of them besides itself).
 __global__ void __launch_bounds__(256)
 densify_apply_kernel(int64_t n, const Tri* __restrict__ flags, const Tri* __restrict__ pos, int64_t kept, int64_t cloned,
-                     int64_t split, ModelPtrs m, const float* __restrict__ noise) {
+                     int64_t split, ModelPtrs m, const float* __restrict__ noise, int32_t* __restrict__ src_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Tri f = flags[i], p = pos[i];
@@ -93,6 +93,7 @@ densify_apply_kernel(int64_t n, const Tri* __restrict__ flags, const Tri* __rest
         copy_row(m.xyz, m.o_xyz, i, d, 3); copy_row(m.dc, m.o_dc, i, d, 3); copy_row(m.rest, m.o_rest, i, d, 45);
         copy_row(m.scaling, m.o_scaling, i, d, 3); copy_row(m.rotation, m.o_rotation, i, d, 4);
         m.o_opacity[d] = m.opacity[i];
+        if (src_row) src_row[d] = (int32_t)i;       // the only rows with a history (optimiser moments follow them)
     }
     if (f.b) {                                      // clone copy: jittered position, everything else equal
         const int64_t d = kept + p.b;
@@ -101,6 +102,7 @@ densify_apply_kernel(int64_t n, const Tri* __restrict__ flags, const Tri* __rest
         copy_row(m.dc, m.o_dc, i, d, 3); copy_row(m.rest, m.o_rest, i, d, 45);
         copy_row(m.scaling, m.o_scaling, i, d, 3); copy_row(m.rotation, m.o_rotation, i, d, 4);
         m.o_opacity[d] = m.opacity[i];
+        if (src_row) src_row[d] = -1;
     }
     if (f.c) {                                      // two children along the first principal axis
         const float4 q = *reinterpret_cast<const float4*>(m.rotation + i * 4);
@@ -124,6 +126,7 @@ densify_apply_kernel(int64_t n, const Tri* __restrict__ flags, const Tri* __rest
             // the unit quaternion the accessor returns (scene.py: rot = get_rotation[mask])
             *reinterpret_cast<float4*>(m.o_rotation + d * 4) = make_float4(w, x, y, z);
             m.o_opacity[d] = co;
+            if (src_row) src_row[d] = -1;
         }
     }
 }
@@ -191,7 +194,7 @@ extern "C" int gs_densify_apply(int64_t n, const void* workspace, int64_t kept, 
                                 const float* xyz, const float* features_dc, const float* features_rest, const float* scaling_log,
                                 const float* rotation, const float* opacity, const float* noise,
                                 float* o_xyz, float* o_features_dc, float* o_features_rest, float* o_scaling_log,
-                                float* o_rotation, float* o_opacity, void* stream) {
+                                float* o_rotation, float* o_opacity, int32_t* src_row, void* stream) {
     GS_REQUIRE(n >= 0 && kept >= 0 && cloned >= 0 && split >= 0, "negative size");
     if (n == 0 || kept + cloned + split == 0) return GS_OK;
     GS_REQUIRE(workspace && xyz && features_dc && features_rest && scaling_log && rotation && opacity, "NULL input array");
@@ -203,7 +206,7 @@ extern "C" int gs_densify_apply(int64_t n, const void* workspace, int64_t kept, 
     ModelPtrs m = {xyz, features_dc, features_rest, scaling_log, rotation, opacity,
                    o_xyz, o_features_dc, o_features_rest, o_scaling_log, o_rotation, o_opacity};
     densify_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        n, (const Tri*)(w + L.flags), (const Tri*)(w + L.pos), kept, cloned, split, m, noise);
+        n, (const Tri*)(w + L.flags), (const Tri*)(w + L.pos), kept, cloned, split, m, noise, src_row);
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
     return GS_OK;

@@ -69,6 +69,28 @@ __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+// The same three operations with a compile-time choice between the packed instruction and two scalar ones (identical
+// IEEE results).  A packed op holds the FP32 pipe for two cycles, so the cycle after it must be filled by a non-FP32
+// instruction; with as many packed ops as other instructions the schedule would have to alternate perfectly.  Running
+// the last GS_*_SCALAR_PAIRS of a lane's four pixel pairs through scalar ops trades issue slots for slack.
+template <bool kPk> __device__ __forceinline__ float2 fma2s(float2 a, float2 b, float2 c) {
+    if (kPk) return __ffma2_rn(a, b, c);
+    return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+}
+template <bool kPk> __device__ __forceinline__ float2 add2s(float2 a, float2 b) {
+    if (kPk) return __fadd2_rn(a, b);
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+template <bool kPk> __device__ __forceinline__ float2 mul2s(float2 a, float2 b) {
+    if (kPk) return __fmul2_rn(a, b);
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+}
+#ifndef GS_FWD_SCALAR_PAIRS
+#define GS_FWD_SCALAR_PAIRS 0
+#endif
+#ifndef GS_BWD_SCALAR_PAIRS
+#define GS_BWD_SCALAR_PAIRS 0
+#endif
 
 // Per-entry values shared by a lane's 8 pixels, pre-broadcast into pairs.
 struct EntryRow {
@@ -108,25 +130,25 @@ __device__ __forceinline__ float live_select(float A, float w, float c) {
     return r;
 }
 
-template <bool kFast>
+template <bool kFast, bool kPk = true>
 __device__ __forceinline__ void eval_pair(float2 fpx, const EntryRow& r, float2 A, PairEval& ev) {
-    ev.dx = add2(fpx, r.neg_mx);
-    const float2 t = fma2(r.q00, ev.dx, r.qsdy);
-    const float2 sp = fma2(ev.dx, t, r.q11dy2);          // -0.5*log2(e) * s
+    ev.dx = add2s<kPk>(fpx, r.neg_mx);
+    const float2 t = fma2s<kPk>(r.q00, ev.dx, r.qsdy);
+    const float2 sp = fma2s<kPk>(ev.dx, t, r.q11dy2);          // -0.5*log2(e) * s
     ev.e = make_float2(ex2_approx(sp.x), ex2_approx(sp.y));
-    ev.T = fma2(A, bc2(-1.0f), bc2(1.0f));                              // 1 - A, one rounding
+    ev.T = fma2s<kPk>(A, bc2(-1.0f), bc2(1.0f));                              // 1 - A, one rounding
     if (kFast) {
         ev.w = make_float2(live_weight(A.x, ev.e.x), live_weight(A.y, ev.e.y));
-        ev.u = mul2(bc2(r.op), ev.w);
+        ev.u = mul2s<kPk>(bc2(r.op), ev.w);
         ev.a = ev.u;
-        ev.contrib = mul2(ev.T, ev.a);
+        ev.contrib = mul2s<kPk>(ev.T, ev.a);
         ev.act0 = ev.w.x > 0.f;
         ev.act1 = ev.w.y > 0.f;
     } else {
         ev.w = make_float2(fminf(ev.e.x, 1.0f), fminf(ev.e.y, 1.0f));      // clamp(exp(.), 0, 1); exp >= 0
-        ev.u = mul2(bc2(r.op), ev.w);
+        ev.u = mul2s<kPk>(bc2(r.op), ev.w);
         ev.a = make_float2(__saturatef(ev.u.x), __saturatef(ev.u.y));      // clamp(opacity * w, 0, 1)
-        const float2 c = mul2(ev.T, ev.a);
+        const float2 c = mul2s<kPk>(ev.T, ev.a);
         // a > 0 and contrib > 0 follow from opacity > kTinyOpacity, w >= 1e-5 and 1 - A >= 0.005;
         // entries with opacity <= kTinyOpacity (or negative) were staged with opacity 0 and contribute
         // exact zeros (a = 0 => contrib = 0; the backward skips such an entry as a whole)
@@ -212,12 +234,21 @@ __device__ __forceinline__ int fwd_batch(const float4* srec, int cnt, int first_
 #pragma unroll
             for (int p = 0; p < kPairs; ++p) {
                 PairEval ev;
-                eval_pair<kFast>(fpx[p], row, A[p], ev);
-                Cr[p] = fma2(ev.contrib, cr, Cr[p]);
-                Cg[p] = fma2(ev.contrib, cg, Cg[p]);
-                Cb[p] = fma2(ev.contrib, cb, Cb[p]);
-                Ds[p] = fma2(ev.contrib, z, Ds[p]);
-                A[p] = add2(A[p], ev.contrib);
+                if (p < kPairs - GS_FWD_SCALAR_PAIRS) {
+                    eval_pair<kFast, true>(fpx[p], row, A[p], ev);
+                    Cr[p] = fma2(ev.contrib, cr, Cr[p]);
+                    Cg[p] = fma2(ev.contrib, cg, Cg[p]);
+                    Cb[p] = fma2(ev.contrib, cb, Cb[p]);
+                    Ds[p] = fma2(ev.contrib, z, Ds[p]);
+                    A[p] = add2(A[p], ev.contrib);
+                } else {
+                    eval_pair<kFast, false>(fpx[p], row, A[p], ev);
+                    Cr[p] = fma2s<false>(ev.contrib, cr, Cr[p]);
+                    Cg[p] = fma2s<false>(ev.contrib, cg, Cg[p]);
+                    Cb[p] = fma2s<false>(ev.contrib, cb, Cb[p]);
+                    Ds[p] = fma2s<false>(ev.contrib, z, Ds[p]);
+                    A[p] = add2s<false>(A[p], ev.contrib);
+                }
                 if (kTrack) {                           // renderer.py:352: the entry that terminates the pixel
                     if (ev.act0 && A[p].x >= kTermA) ncons[2 * p] = first_index + j + 1;
                     if (ev.act1 && A[p].y >= kTermA) ncons[2 * p + 1] = first_index + j + 1;
@@ -404,6 +435,56 @@ __device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id
     }
 }
 
+// Per-lane partial sums of one list entry over the lane's pixels.
+struct BwdAcc {
+    float2 s_h, s_x, s_xx, s_op, s_z, s_cr, s_cg, s_cb;
+};
+
+// Backward arithmetic of one list entry for ONE pixel pair (kPk: packed or scalar FP32 instructions, same results).
+template <bool kFast, bool kPk>
+__device__ __forceinline__ void bwd_pair(float2 fpx, const EntryRow& row, float2& A, float2& R, float2 gCr, float2 gCg, float2 gCb,
+                                         float2 gDs, float2 gA, float2 cr, float2 cg, float2 cb, float2 z, BwdAcc& acc) {
+    PairEval ev;
+    eval_pair<kFast, kPk>(fpx, row, A, ev);
+    const float2 v = fma2s<kPk>(gCr, cr, fma2s<kPk>(gCg, cg, fma2s<kPk>(gCb, cb, fma2s<kPk>(gDs, z, gA))));
+    R = fma2s<kPk>(ev.contrib, v, R);
+    A = add2s<kPk>(A, ev.contrib);
+    // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
+    // a < 0.995, so 1 - a >= 0.005 and the approximate reciprocal is safe (a pixel that this
+    // entry terminates may see 1 - a ~ 0: its inf/NaN is discarded by the select).
+    const float2 oma = fma2s<kPk>(ev.a, bc2(-1.0f), bc2(1.0f));
+    float2 nsuf = mul2s<kPk>(R, make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
+    nsuf.x = (A.x >= kTermA) ? 0.f : nsuf.x;
+    nsuf.y = (A.y >= kTermA) ? 0.f : nsuf.y;
+    float2 g_a = fma2s<kPk>(ev.T, v, nsuf);
+    if (kFast) {
+        // ev.w is already zero where the reference skips the splat, and g_a only ever appears multiplied
+        // by it, so no further masking (both clamps are identities on this path).  dL/ds' = ln2*op*(w*g_a):
+        // the constant factor is applied once per entry, which also makes sum(h) the opacity sum itself.
+        const float2 gw = mul2s<kPk>(g_a, ev.w);
+        const float2 gwdx = mul2s<kPk>(gw, ev.dx);
+        acc.s_op = add2s<kPk>(acc.s_op, gw);
+        acc.s_x = add2s<kPk>(acc.s_x, gwdx);
+        acc.s_xx = fma2s<kPk>(gwdx, ev.dx, acc.s_xx);
+    } else {
+        // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
+        g_a.x = (ev.act0 && ev.u.x <= 1.f) ? g_a.x : 0.f;
+        g_a.y = (ev.act1 && ev.u.y <= 1.f) ? g_a.y : 0.f;
+        float2 h = mul2s<kPk>(ev.w, g_a);
+        acc.s_op = add2s<kPk>(acc.s_op, h);
+        h.x = (ev.e.x <= 1.f) ? h.x : 0.f;
+        h.y = (ev.e.y <= 1.f) ? h.y : 0.f;
+        const float2 hdx = mul2s<kPk>(h, ev.dx);
+        acc.s_h = add2s<kPk>(acc.s_h, h);
+        acc.s_x = add2s<kPk>(acc.s_x, hdx);
+        acc.s_xx = fma2s<kPk>(hdx, ev.dx, acc.s_xx);
+    }
+    acc.s_cr = fma2s<kPk>(ev.contrib, gCr, acc.s_cr);
+    acc.s_cg = fma2s<kPk>(ev.contrib, gCg, acc.s_cg);
+    acc.s_cb = fma2s<kPk>(ev.contrib, gCb, acc.s_cb);
+    acc.s_z = fma2s<kPk>(ev.contrib, gDs, acc.s_z);
+}
+
 // Arithmetic of ONE list entry for this lane's 8 pixels; leaves the 10 per-lane partial sums in
 // rb[v * kRedStride + lane] (first half of the transpose reduction).  No barrier inside.
 template <bool kFast>
@@ -419,50 +500,17 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
     float dy;
     load_entry_row(r0, r1, fpy, row, dy);
     const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
-    float2 s_h = bc2(0.f), s_x = bc2(0.f), s_xx = bc2(0.f), s_op = bc2(0.f), s_z = bc2(0.f);
-    float2 s_cr = bc2(0.f), s_cg = bc2(0.f), s_cb = bc2(0.f);
+    BwdAcc acc;
+    acc.s_h = acc.s_x = acc.s_xx = acc.s_op = acc.s_z = acc.s_cr = acc.s_cg = acc.s_cb = bc2(0.f);
 #pragma unroll
     for (int p = 0; p < kPairs; ++p) {
-        PairEval ev;
-        eval_pair<kFast>(fpx[p], row, A[p], ev);
-        const float2 v = fma2(gCr[p], cr, fma2(gCg[p], cg, fma2(gCb[p], cb, fma2(gDs[p], z, gA[p]))));
-        R[p] = fma2(ev.contrib, v, R[p]);
-        A[p] = add2(A[p], ev.contrib);
-        // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
-        // a < 0.995, so 1 - a >= 0.005 and the approximate reciprocal is safe (a pixel that this
-        // entry terminates may see 1 - a ~ 0: its inf/NaN is discarded by the select).
-        const float2 oma = fma2(ev.a, bc2(-1.0f), bc2(1.0f));
-        float2 nsuf = mul2(R[p], make_float2(rcp_approx(oma.x), rcp_approx(oma.y)));
-        nsuf.x = (A[p].x >= kTermA) ? 0.f : nsuf.x;
-        nsuf.y = (A[p].y >= kTermA) ? 0.f : nsuf.y;
-        float2 g_a = fma2(ev.T, v, nsuf);
-        if (kFast) {
-            // ev.w is already zero where the reference skips the splat, and g_a only ever appears multiplied
-            // by it, so no further masking (both clamps are identities on this path).  dL/ds' = ln2*op*(w*g_a):
-            // the constant factor is applied once per entry, which also makes sum(h) the opacity sum itself.
-            const float2 gw = mul2(g_a, ev.w);
-            const float2 gwdx = mul2(gw, ev.dx);
-            s_op = add2(s_op, gw);
-            s_x = add2(s_x, gwdx);
-            s_xx = fma2(gwdx, ev.dx, s_xx);
-        } else {
-            // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
-            g_a.x = (ev.act0 && ev.u.x <= 1.f) ? g_a.x : 0.f;
-            g_a.y = (ev.act1 && ev.u.y <= 1.f) ? g_a.y : 0.f;
-            float2 h = mul2(ev.w, g_a);
-            s_op = add2(s_op, h);
-            h.x = (ev.e.x <= 1.f) ? h.x : 0.f;
-            h.y = (ev.e.y <= 1.f) ? h.y : 0.f;
-            const float2 hdx = mul2(h, ev.dx);
-            s_h = add2(s_h, h);
-            s_x = add2(s_x, hdx);
-            s_xx = fma2(hdx, ev.dx, s_xx);
-        }
-        s_cr = fma2(ev.contrib, gCr[p], s_cr);
-        s_cg = fma2(ev.contrib, gCg[p], s_cg);
-        s_cb = fma2(ev.contrib, gCb[p], s_cb);
-        s_z = fma2(ev.contrib, gDs[p], s_z);
+        if (p < kPairs - GS_BWD_SCALAR_PAIRS)
+            bwd_pair<kFast, true>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
+        else
+            bwd_pair<kFast, false>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
     }
+    const float2 s_h = acc.s_h, s_x = acc.s_x, s_xx = acc.s_xx, s_op = acc.s_op, s_z = acc.s_z;
+    const float2 s_cr = acc.s_cr, s_cg = acc.s_cg, s_cb = acc.s_cb;
     // an entry staged with opacity 0 (<= kTinyOpacity, or negative) is one the reference skips (a <= 0):
     // every sum below is then an exact zero except the opacity one, which is forced to zero
     const float Sop_all = s_op.x + s_op.y;

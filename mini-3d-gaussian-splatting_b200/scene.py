@@ -320,8 +320,9 @@ class GaussianModel(nn.Module):
             if noise.shape[0] < candidates:
                 raise ValueError(f"noise has {noise.shape[0]} rows, {candidates} splats meet the clone criterion")
             out = [torch.empty((total,) + tuple(p.shape[1:]), dtype=torch.float32, device=dev) for p in params]
+            src_row = torch.empty(total, dtype=torch.int32, device=dev)
             _lib.check(lib.gs_densify_apply(n, _lib.ptr(ws), kept, cloned, split, *[_lib.ptr(p) for p in params], _lib.ptr(noise),
-                                            *[_lib.ptr(o) for o in out], stream), "gs_densify_apply")
+                                            *[_lib.ptr(o) for o in out], _lib.ptr(src_row), stream), "gs_densify_apply")
         self._set(*out)
-        return {"kept": kept, "cloned": cloned, "split": split, "points": total}
+        return {"kept": kept, "cloned": cloned, "split": split, "points": total, "src_row": src_row}
 

@@ -81,6 +81,37 @@ class GaussianOptimizer:
         fused = all(g["params"][0].is_cuda for g in groups)
         self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15, fused=fused)
 
+    @torch.no_grad()
+    def carry_state(self, src_row: torch.Tensor) -> None:
+        """Rebuild Adam on the model's new parameters after a densification round and CARRY the moments over:
+        row j of every new exp_avg / exp_avg_sq is the old row `src_row[j]`, or zero where `src_row[j] < 0` (clone
+        copies and split children start without history, as appended rows do in the original 3DGS trainer); the step
+        counts and learning rates are kept.  The reference's intent at optimizer.py:67-71 is the cruder `rebuild()`
+        (state cleared); SURVEY 8f rank 1 asks for the carry-over."""
+        old = self.optimizer
+        saved = {g["name"]: (g["lr"], dict(old.state.get(g["params"][0], {}))) for g in old.param_groups}
+        self.rebuild()
+        src_row = src_row.to(torch.int64)
+        dst = torch.nonzero(src_row >= 0, as_tuple=False).squeeze(-1)
+        src = src_row[dst]
+        for g in self.optimizer.param_groups:
+            lr, st = saved[g["name"]]
+            g["lr"] = lr
+            if not st:
+                continue
+            p = g["params"][0]
+            if p.shape[0] != src_row.shape[0]:
+                raise ValueError(f"src_row has {src_row.shape[0]} rows, parameter {g['name']} has {p.shape[0]}")
+            new = {}
+            for k, v in st.items():
+                if torch.is_tensor(v) and v.dim() > 0 and v.shape[1:] == p.shape[1:]:
+                    t = torch.zeros_like(p)
+                    t[dst] = v.to(p.device)[src.to(v.device)]
+                    new[k] = t
+                else:
+                    new[k] = v.clone() if torch.is_tensor(v) else v       # the step counter
+            self.optimizer.state[p] = new
+
     def update_learning_rate(self, iteration: int) -> float:
         lr = self.xyz_scheduler.get_lr(iteration)
         for g in self.optimizer.param_groups:
@@ -96,9 +127,18 @@ class GaussianOptimizer:
 
 
 class DensityController:
-    def __init__(self, config: Optional[TrainingConfig] = None, fused: bool = True):
+    def __init__(self, config: Optional[TrainingConfig] = None, fused: bool = True, carry_state: bool = True):
         self.config = config or TrainingConfig()
         self.fused = fused           # CUDA models: gs_densify_plan / gs_densify_apply instead of tensor ops
+        self.carry_state = carry_state   # False: the optimiser forgets its moments at every round (optimizer.py:67-71)
+
+    def _refresh_optimizer(self, optimizer, src_row) -> None:
+        if optimizer is None:
+            return
+        if self.carry_state:
+            optimizer.carry_state(src_row)
+        else:
+            optimizer.rebuild()
 
     def should_densify(self, iteration: int) -> bool:
         c = self.config
@@ -119,31 +159,36 @@ class DensityController:
             # except "pruned", which here counts only originals (a pruned clone/child was never created)
             n0 = model.get_num_points()
             r = model.densify_fused(g, th, scene_extent, 0.01, generator=generator)
-            if optimizer is not None:
-                optimizer.rebuild()
-            return {"split": r["split"], "cloned": r["cloned"], "pruned": n0 - r["kept"] - r["split"], "points": r["points"]}
+            self._refresh_optimizer(optimizer, r["src_row"])
+            return {"split": r["split"], "cloned": r["cloned"], "pruned": n0 - r["kept"] - r["split"], "points": r["points"],
+                    "src_row": r["src_row"]}
         gn = g.norm(dim=-1)
         sig = model.get_scaling.mean(dim=-1)
         clone_mask = (gn > th) & (sig < 0.01 * scene_extent)
         split_mask = (gn > th) & (sig > 0.03 * scene_extent)
         # clone first: appended rows do not disturb the indices the split mask refers to
         n0 = model.get_num_points()
+        # where every row of the new model comes from: the original's index, or -1 for rows created here
+        src_row = torch.arange(n0, device=g.device, dtype=torch.int64)
+        fresh = lambda k: torch.full((k,), -1, device=g.device, dtype=torch.int64)  # noqa: E731
         cloned = model.density_and_clone(th, scene_extent, grad=g, generator=generator)
         if cloned:
             split_mask = torch.cat([split_mask, torch.zeros(cloned, dtype=torch.bool, device=split_mask.device)])
             g = torch.cat([g, torch.zeros(cloned, 3, device=g.device, dtype=g.dtype)])
+            src_row = torch.cat([src_row, fresh(cloned)])
         split = 0
         if bool(split_mask.any()):
             g_for_split = torch.where(split_mask.unsqueeze(-1), g, torch.zeros_like(g))
             split = model.density_and_split(th, scene_extent, grad=g_for_split)
+            src_row = torch.cat([src_row[~split_mask], fresh(2 * split)])
         keep = model.get_opacity.squeeze(1) > 0.01
         pruned = int((~keep).sum())
         if pruned:
             model.prune_points(keep)
-        if optimizer is not None:
-            optimizer.rebuild()
-        assert int(clone_mask.sum()) == cloned and n0 + cloned + split - pruned == model.get_num_points()
-        return {"split": split, "cloned": cloned, "pruned": pruned, "points": model.get_num_points()}
+            src_row = src_row[keep]
+        self._refresh_optimizer(optimizer, src_row)
+        assert int(clone_mask.sum()) == cloned and n0 + cloned + split - pruned == model.get_num_points() == src_row.shape[0]
+        return {"split": split, "cloned": cloned, "pruned": pruned, "points": model.get_num_points(), "src_row": src_row}
 
 
 def l1_loss(image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -265,13 +265,81 @@ def make_stage_fixture(n=200000, seed=0):
             ref_rect=torch.stack([tx0, tx1, ty0, ty1], 1).numpy().astype(np.int16), ref_cnt=cnt.numpy().astype(np.int16))
 
 
+def make_densify_fixture(n=1500, seed=61):
+    """Density control through the reference's OWN functions -- GaussianModel.density_and_clone, density_and_split and
+    prune_points (src/core/gaussian_model.py:130-197) -- on a seeded model, with the `_append_points` patch of the
+    reference's own test (tests/test_gaussian_model.py:103-111: the stock method reads a non-existent `_scaling_log`).
+    Driver order = the one mini-3d-gaussian-splatting_b200.training.DensityController uses: both masks from the same
+    pre-densification gradient, clone first (appended rows do not disturb the split indices), then split, then the opacity
+    prune of optimizer.py:64-66 (whose `get_opacity()` call is itself a bug: the property is read here)."""
+    import types
+    import torch.nn as nn
+    GaussianRenderer, RenderSettings, GaussianModel, TrainingConfig = import_reference()
+    s = so.scene_aniso(n, seed)
+    g = torch.Generator().manual_seed(7)
+    sc = s["scaling"].clone()
+    sc[: n // 3] = math.log(0.05) + 0.1 * torch.randn(n // 3, 3, generator=g)              # large  -> split candidates
+    sc[n // 3: 2 * n // 3] = math.log(0.004) + 0.1 * torch.randn(n // 3, 3, generator=g)   # small  -> clone candidates
+    op = s["opacity"].clone()
+    op[::7] = -9.0                                         # transparent -> pruned (also as clone copies / children)
+    op[5::11] = 8.0                                        # children's logit is clamped to 6
+    grad = torch.zeros(n, 3)
+    hot = torch.rand(n, generator=g) < 0.6
+    grad[hot] = 1.0 + torch.rand(int(hot.sum()), 3, generator=g)
+    rest = 0.1 * torch.randn(n, 15, 3, generator=g)
+    th, extent, min_opacity, noise_seed = 0.5, 1.0, 0.01, 3
+
+    m = GaussianModel(TrainingConfig())
+    P = nn.Parameter
+    m._xyz, m._features_dc, m._features_rest = P(s["xyz"].clone()), P(s["features_dc"].clone()), P(rest.clone())
+    m._scaling, m._rotation, m._opacity = P(sc.clone()), P(s["rotation"].clone()), P(op.clone())
+
+    def _append_points_patch(self, xyz, fdc, frest, scaling_log, rot, op_):       # tests/test_gaussian_model.py:103-111
+        self._xyz = nn.Parameter(torch.cat([self._xyz.data, xyz], dim=0))
+        self._features_dc = nn.Parameter(torch.cat([self._features_dc.data, fdc], dim=0))
+        self._features_rest = nn.Parameter(torch.cat([self._features_rest.data, frest], dim=0))
+        self._scaling = nn.Parameter(torch.cat([self._scaling.data, scaling_log], dim=0))
+        self._rotation = nn.Parameter(torch.cat([self._rotation.data, rot], dim=0))
+        self._opacity = nn.Parameter(torch.cat([self._opacity.data, op_], dim=0))
+    m._append_points = types.MethodType(_append_points_patch, m)
+
+    size = m.get_scaling.mean(dim=-1)
+    clone_mask = (grad.norm(dim=-1) > th) & (size < 0.01 * extent)
+    split_mask = (grad.norm(dim=-1) > th) & (size > 0.03 * extent)
+    k = int(clone_mask.sum())
+    torch.manual_seed(noise_seed)
+    noise = torch.randn(k, 3)                              # the block density_and_clone's randn_like draws next
+    torch.manual_seed(noise_seed)
+    m._xyz.grad = grad.clone()
+    m.density_and_clone(th, extent)                        # reference code
+    assert m.get_num_points() == n + k
+    g2 = torch.cat([torch.where(split_mask.unsqueeze(-1), grad, torch.zeros_like(grad)), torch.zeros(k, 3)])
+    m._xyz.grad = g2
+    m.density_and_split(th, extent)                        # reference code
+    n_split = int(split_mask.sum())
+    assert m.get_num_points() == n + k + n_split
+    keep = m.get_opacity.squeeze(1) > min_opacity          # optimizer.py:64 (property, not a call)
+    m.prune_points(keep)                                   # reference code
+    print(f"[densify] n={n}: {k} clone candidates, {n_split} split candidates, {int((~keep).sum())} rows pruned -> {m.get_num_points()} rows")
+    np.savez_compressed(
+        os.path.join(HERE, f"densify_n{n}.npz"),
+        th=np.array(th), extent=np.array(extent), min_opacity=np.array(min_opacity),
+        in_xyz=s["xyz"].numpy(), in_features_dc=s["features_dc"].numpy(), in_features_rest=rest.numpy(), in_scaling=sc.numpy(),
+        in_rotation=s["rotation"].numpy(), in_opacity=op.numpy(), in_grad=grad.numpy(), noise=noise.numpy(),
+        n_clone_candidates=np.array(k), n_split_candidates=np.array(n_split),
+        ref_xyz=m._xyz.data.numpy(), ref_features_dc=m._features_dc.data.numpy(), ref_features_rest=m._features_rest.data.numpy(),
+        ref_scaling=m._scaling.data.numpy(), ref_rotation=m._rotation.data.numpy(), ref_opacity=m._opacity.data.numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    want = sys.argv[1:] or (["kat", "stages"] + list(CASES))
+    want = sys.argv[1:] or (["kat", "stages", "densify"] + list(CASES))
     for c in want:
         if c == "kat":
             make_kat_two_splats()
         elif c == "stages":
             make_stage_fixture()
+        elif c == "densify":
+            make_densify_fixture()
         else:
             make_case(c)
