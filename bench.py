@@ -306,11 +306,20 @@ def main():
             single = mv.FlatGradBuffer(model, peer=False)
             cams_all = [gb.Camera.orbit(r, world, WIDTH, HEIGHT) for r in range(world)]
             mv.multiview_step(model, rd, cams_all, settings, view_loss, buffer=single, reduce=False)
-            per_seg = {}
+            per_seg, mags = {}, {}
             for (name, a), (_, b) in zip(seg_tensors(buf), seg_tensors(single)):
                 per_seg[name] = float((a - b).abs().max() / (b.abs().max() + 1e-30))
-            exchange_check["max_rel_err_vs_1gpu_sum"] = max(per_seg.values())
-            exchange_check["rel_err_vs_1gpu_sum_per_segment"] = per_seg
+                mags[name] = float(b.abs().max())
+            # the ref-init scene is isotropic: the covariance does not depend on the rotation, so its "gradient" is rounding
+            # noise (~1e-11) whose relative error means nothing; it is reported as an absolute error next to its
+            # magnitude and left out of the headline figure
+            noise = [k for k in per_seg if k == "rotation" and mags[k] < 1e-6 * mags["xyz"]]
+            exchange_check["max_rel_err_vs_1gpu_sum"] = max(v for k, v in per_seg.items() if k not in noise)
+            exchange_check["rel_err_vs_1gpu_sum_per_segment"] = {k: v for k, v in per_seg.items() if k not in noise}
+            if noise:
+                a, b = dict(seg_tensors(buf))["rotation"], dict(seg_tensors(single))["rotation"]
+                exchange_check["rotation_gradient_is_rounding_noise"] = {
+                    "max_abs_1gpu": mags["rotation"], "max_abs_err": float((a - b).abs().max()), "max_abs_xyz_gradient": mags["xyz"]}
             exchange_check["what"] = (f"{world} orbit views: (a) each rank's local buffer reduced by the product's exchange vs NCCL all_reduce "
                                       "SUM/MAX of the same inputs; (b) the exchanged result vs the same views rendered and accumulated on rank 0 "
                                       "alone (max|a-b|/max|b| per buffer segment); (c) torch.equal of the full buffer across ranks")
@@ -392,14 +401,24 @@ def main():
     T = rd._last_debug["tile_ranges"].shape[0]
     E = int(rd._last_debug["tile_consumed"].sum().item())
     P = WIDTH * HEIGHT
-    # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
+    # algorithmic bytes per launch of what actually runs
+    Vb = st["num_binned"]
+    lens = (rd._last_debug["tile_ranges"][:, 1] - rd._last_debug["tile_ranges"][:, 0]).long()
+    stored = int(lens.clamp(max=int(rd.list_cap)).sum().item()) if rd.list_cap else D       # entries the scatter stores
+    chunks, row_tiles = -(-Vb // 255), -(-T // 128) * 128
+    sort_passes = 3                                            # 8-bit passes over the differing key bits (24 here)
     alg = {
         "project_fwd": n * (56 + 109),                       # xyz 12+scale 12+quat 16+opacity 4+dc 12 ; outputs 109
-        "bin_prepare": n * (4 + 8 * 4 * 2 + 4 + 8 + 8),       # iota, 4 radix passes over (key,id), gather, scan
-        "bin_sort": n * 28 + D * 8 + D * (4 + 2 * 16) + D * 4 + T * 8,   # duplicate, 2 radix passes of (key,id) + histogram, ranges
+        # depth sort: key range pass 4N; pass 1 reads keys, later passes (key,id); every pass but the last writes (key,id);
+        # the last gathers tiles_touched and writes sorted ids 4N + offsets 8N
+        "bin_prepare": n * (4 + 4 + 8 * (sort_passes - 1) + 8 * (sort_passes - 1) + 4 + 4 + 8),
+        # counting sort on the tile id: ids+offsets+rectangles of the binned splats, twice (walk, scatter); one byte per
+        # pair written and read (count-so-far); the [chunks x tiles] count (1 B) and prefix (2 B) tables written and read;
+        # 4 B per stored list entry; tile ranges
+        "bin_sort": Vb * (16 + 8) + 2 * D + 2 * 3 * chunks * row_tiles + 4 * stored + 8 * T,
         "raster_fwd": T * 12 + E * 52 + P * 40,
         "raster_bwd": T * 12 + E * 52 + E * 44 + P * 40,
-        "project_bwd": n * (56 + 44 + 56),
+        "project_bwd": n * (56 + 44 + 56 + 17),              # parameters, incoming gradients, outgoing gradients, statistics
     }
     hbm_peak, peak_src = measured_peaks()
     kernels = {k: {"ms": per[k], "alg_bytes": alg[k], "gbs": alg[k] / (per[k] * 1e-3) / 1e9,

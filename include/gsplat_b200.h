@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 15
+#define GS_ABI_VERSION 17
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -175,7 +175,10 @@ int gs_project_bwd(int64_t n,
  * Outputs: entry_ids [D] int32 splat ids grouped by tile, front to back;
  *          tile_ranges [num_tiles,2] int32 = [begin,end) into entry_ids;
  *          entry_keys [D] uint64 (optional, may be NULL) = tile_id<<32 | depth_bits of each entry,
- *          for parity checks against the reference order.
+ *          for parity checks against the reference order;
+ *          tile_order [num_tiles] int32 (optional, flat counting sort only; ignored by the other algorithms): the tiles
+ *          sorted by decreasing list length (buckets of 8 entries) -- what gs_tile_order(tile_ranges) would give, produced
+ *          by the same launch that scans the tiles.
  * ------------------------------------------------------------------------------------- */
 #define GS_BIN_AUTO 0
 #define GS_BIN_COUNTING 1
@@ -197,7 +200,7 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
                 void* workspace, int64_t workspace_bytes,
                 int32_t* entry_ids, int32_t* tile_ranges, uint64_t* entry_keys,
                 const int64_t* counters_dev, int32_t list_cap,
-                void* stream);
+                int32_t* tile_order, void* stream);
 
 /* Truncated tile lists (flat counting sort only).  With list_cap > 0 gs_bin_sort stores only the first list_cap
  * entries of every tile's list (tile_ranges still describe the complete lists); gs_raster_fwd, given the same
@@ -275,10 +278,13 @@ int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
  * that all ranks' results have landed before anyone reads.  Results are bit-identical on all ranks.
  * multicast_ptr: 0, or the NVSwitch multicast address of the same buffers; then the reduction runs inside
  * the switch (multimem.ld_reduce / multimem.st) and the MAX region must hold non-negative floats.
+ * flags: GS_PEER_TMA moves the data with bulk asynchronous copies (cp.async.bulk global<->shared, mbarrier completion,
+ * a 3-stage ring of 64 KB per CTA) instead of per-thread 16-byte loads/stores; same owner, same summation order, same bits.
  * ------------------------------------------------------------------------------------- */
+#define GS_PEER_TMA 1
 int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int32_t world, int32_t rank,
                       int64_t sum_offset, int64_t sum_count, int64_t max_offset, int64_t max_count,
-                      void* stream);
+                      int32_t flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Density control on the device: GaussianModel.density_and_split / density_and_clone / prune_points

@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
-ABI_VERSION = 15
+ABI_VERSION = 17
 LIB_NAME = "libgsplat_b200.so"
 # GSPLAT_B200_LIB points at an alternative build of the same ABI (kernel-variant experiments, tools/)
 LIB_PATH = os.environ.get("GSPLAT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
@@ -31,11 +31,11 @@ SIGNATURES = {
     "gs_densify_plan": (c_int32, [c_int64, _P, _P, _P, c_float, c_float, c_float, c_float, _P, c_int64, _P, _P]),
     "gs_densify_apply": (c_int32, [c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P]),
-    "gs_peer_allreduce": (c_int32, [_P, ctypes.c_uint64, c_int32, c_int32, c_int64, c_int64, c_int64, c_int64, _P]),
+    "gs_peer_allreduce": (c_int32, [_P, ctypes.c_uint64, c_int32, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32, _P]),
     "gs_bin_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
     "gs_bin_prepare": (c_int32, [c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
     "gs_bin_sort": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,
-                               _P, c_int64, _P, _P, _P, _P, c_int32, _P]),
+                               _P, c_int64, _P, _P, _P, _P, c_int32, _P, _P]),
     "gs_bin_complete": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, c_int32, c_int32, _P, c_int64,
                                    c_int32, _P, _P, _P, _P, _P]),
     "gs_raster_fwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P,

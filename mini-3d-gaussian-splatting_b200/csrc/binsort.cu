@@ -376,6 +376,150 @@ close_chunk_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, co
     atomicMax(&close_chunk[(ty / kCloseBlk) * blocks_x + tx / kCloseBlk], lo);
 }
 
+__global__ void identity_order_kernel(int num_tiles, int32_t* __restrict__ tile_order) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < num_tiles) tile_order[t] = t;
+}
+
+// 3 (fused).  super_prefix + close_chunk + tile_scan + the forward's longest-first tile order in ONE launch.
+// These were four latency-bound launches of 6-10 us each (a fifth of gs_bin_sort).  Phase 1 runs on every CTA, one thread
+// per tile: exclusive prefix over the super-chunks (in place), the tile's total, and -- truncated lists -- the binary search
+// for the chunk from which the tile's stored prefix is full.  The CTA that finishes last (ticket counter) then does the two
+// single-CTA steps on the totals all CTAs have published: the exclusive scan over tiles (tile_start / tile_ranges) and the
+// bucket sort of the tiles by list length (tile_order, heaviest first).
+constexpr int kTablesThreads = 256;
+constexpr int kOrderBuckets2 = 256;
+__global__ void __launch_bounds__(kTablesThreads)
+tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, const uint16_t* __restrict__ base16,
+                   uint32_t* __restrict__ super_tab, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ tile_start,
+                   int32_t* __restrict__ ranges, uint32_t limit, int blocks_x, int32_t* __restrict__ close_chunk,
+                   int32_t* __restrict__ tile_order, unsigned int* __restrict__ done_counter) {
+    __shared__ int s_cnt[kOrderBuckets2];
+    __shared__ int s_off[kOrderBuckets2];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + tid;
+    int64_t num_sorted;
+    if (!resolve_sizes(sizes, num_sorted)) {
+        // capacity overflow: no list is written (tile_ranges stay zero) and the caller repeats the stage with exact sizes, but
+        // the compositing launch already enqueued behind this one still reads the order: give it a valid one
+        if (tile_order != nullptr && t < num_tiles) tile_order[t] = t;
+        return;
+    }
+    const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
+    const int num_supers = (num_chunks + kSuper - 1) / kSuper;
+    if (t < row_tiles) {
+        uint32_t run = 0u;
+        int sidx = 0;
+        for (; sidx + 8 <= num_supers; sidx += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = super_tab[(int64_t)(sidx + q) * row_tiles + t];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                super_tab[(int64_t)(sidx + q) * row_tiles + t] = run;
+                run += v[q];
+            }
+        }
+        for (; sidx < num_supers; ++sidx) {
+            const uint32_t v = super_tab[(int64_t)sidx * row_tiles + t];
+            super_tab[(int64_t)sidx * row_tiles + t] = run;
+            run += v;
+        }
+        tile_total[t] = run;
+        if (close_chunk != nullptr && t < num_tiles) {
+            int lo = 0, hi = num_chunks;                      // first c in [0, num_chunks] with before(c, t) >= limit
+            if (run < limit) lo = num_chunks;                 // the whole list fits the stored prefix: never closed
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t before = super_tab[(int64_t)(mid / kSuper) * row_tiles + t] + (uint32_t)base16[(int64_t)mid * row_tiles + t];
+                if (before >= limit) hi = mid; else lo = mid + 1;
+            }
+            const int ty = t / tiles_x, tx = t - ty * tiles_x;
+            atomicMax(&close_chunk[(ty / kCloseBlk) * blocks_x + tx / kCloseBlk], lo);
+        }
+    }
+    // ---- the last CTA to get here owns the two single-CTA steps ----------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan over tiles, 256 x 8 tiles per round: every thread loads its 8 consecutive totals up front (independent
+    // loads), scans them locally, the 256 thread sums are scanned by warp shuffles, a carry links the rounds
+    constexpr int kPer = 8;
+    __shared__ uint32_t s_warp[kTablesThreads / 32];
+    __shared__ uint32_t s_carry;
+    const int lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0u;
+    if (tile_order != nullptr && tid < kOrderBuckets2) s_cnt[tid] = 0;
+    __syncthreads();
+    auto bucket = [&](uint32_t len) { return kOrderBuckets2 - 1 - min(kOrderBuckets2 - 1, (int)(len >> 3)); };
+    for (int base = 0; base < num_tiles; base += kTablesThreads * kPer) {
+        const int u0 = base + tid * kPer;
+        uint32_t v[kPer], sum = 0u;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            v[q] = (u0 + q < num_tiles) ? __ldcg(&tile_total[u0 + q]) : 0u;
+            sum += v[q];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0u, round_total = 0u;
+#pragma unroll
+        for (int w = 0; w < kTablesThreads / 32; ++w) {
+            const uint32_t x = s_warp[w];
+            wbase += (w < wid) ? x : 0u;
+            round_total += x;
+        }
+        uint32_t begin = s_carry + wbase + inc - sum;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int u = u0 + q;
+            if (u < num_tiles) {
+                tile_start[u] = begin;
+                reinterpret_cast<int2*>(ranges)[u] = v[q] ? make_int2((int)begin, (int)(begin + v[q])) : make_int2(0, 0);   // empty: (0,0)
+                if (tile_order != nullptr) atomicAdd(&s_cnt[bucket(v[q])], 1);
+            }
+            begin += v[q];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += round_total;
+        __syncthreads();
+    }
+    if (tile_order == nullptr) return;
+    if (tid < 32) {                                           // exclusive scan of the 256 bucket counts by one warp, 8 per lane
+        int local[kOrderBuckets2 / 32], acc = 0;
+#pragma unroll
+        for (int q = 0; q < kOrderBuckets2 / 32; ++q) { local[q] = acc; acc += s_cnt[tid * (kOrderBuckets2 / 32) + q]; }
+        int inc = acc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += x;
+        }
+#pragma unroll
+        for (int q = 0; q < kOrderBuckets2 / 32; ++q) s_off[tid * (kOrderBuckets2 / 32) + q] = inc - acc + local[q];
+    }
+    __syncthreads();
+    for (int base = 0; base < num_tiles; base += kTablesThreads * kPer) {
+        const int u0 = base + tid * kPer;
+        uint32_t v[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) v[q] = (u0 + q < num_tiles) ? __ldcg(&tile_total[u0 + q]) : 0u;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+            if (u0 + q < num_tiles) tile_order[atomicAdd(&s_off[bucket(v[q])], 1)] = u0 + q;
+    }
+}
+
 // 4. parallel scatter in rank order.  One warp per 32 consecutive ranks; for each rank the lanes serve
 // its tiles side by side, so the table reads of a rectangle row and the local_pos read are coalesced.
 // Measured floor: the 26 M four-byte stores land in 26 M different 32-byte sectors and the kernel runs
@@ -471,7 +615,7 @@ static CountLayout count_layout(int64_t num_sorted_cap, int64_t d, int32_t num_t
     L.tile_total = o; o += align_up((int64_t)L.row_tiles * 4, 256);
     L.tile_start = o; o += align_up((int64_t)L.row_tiles * 4, 256);
     L.local_pos = o;  o += align_up(d, 256);
-    L.close_chunk = o; o += align_up(((int64_t)num_tiles / kCloseBlk + 2) * 4, 256);     // >= blocks of any grid shape
+    L.close_chunk = o; o += align_up(((int64_t)num_tiles / kCloseBlk + 2) * 4, 256) + 256;   // ticket counter (first 256 B) + >= blocks of any grid shape
     L.total = o;
     return L;
 }
@@ -817,7 +961,7 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
                            const uint16_t* tile_rect, const uint32_t* depth_keys, int32_t tiles_x, int32_t num_tiles,
                            int32_t algo, void* workspace, int64_t workspace_bytes, int32_t* entry_ids,
                            int32_t* tile_ranges, uint64_t* entry_keys, const int64_t* counters_dev, int32_t list_cap,
-                           void* stream) {
+                           int32_t* tile_order, void* stream) {
     GS_REQUIRE(n >= 0 && num_sorted >= 0 && num_sorted <= n && d >= 0, "bad sizes");
     GS_REQUIRE(num_tiles > 0 && tiles_x > 0, "bad tile grid");
     GS_REQUIRE(tile_ranges != nullptr, "tile_ranges is NULL");
@@ -825,8 +969,16 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(tile_ranges);
     GS_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st));
-    if (counters_dev == nullptr && (d == 0 || num_sorted == 0)) return GS_OK;
-    if (counters_dev != nullptr && (d == 0 || n == 0)) return GS_OK;      // no capacity: nothing can be written
+    const bool nothing = (counters_dev == nullptr && (d == 0 || num_sorted == 0)) ||
+                         (counters_dev != nullptr && (d == 0 || n == 0));      // no pairs / no capacity: nothing can be written
+    if (nothing) {
+        if (tile_order != nullptr) {                    // all lists are empty: any permutation is the longest-first order
+            identity_order_kernel<<<(num_tiles + 255) / 256, 256, 0, st>>>(num_tiles, tile_order);
+            GS_CUDA_TRY(cudaGetLastError());
+            count_launches(1);
+        }
+        return GS_OK;
+    }
     GS_REQUIRE(sorted_ids && offsets && tile_rect && workspace && entry_ids, "NULL array argument");
     GS_REQUIRE(entry_keys == nullptr || depth_keys != nullptr, "entry_keys needs depth_keys");
     GS_REQUIRE(algo >= 0 && algo <= 3, "algo must be 0 (auto), 1 (counting), 2 (radix) or 3 (blocked)");
@@ -915,21 +1067,25 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
         column_prefix_kernel<<<dim3(C.row_tiles / kRowAlign, C.num_supers), dim3(32, 32), 0, st>>>(
             sizes, C.row_tiles, counts, base16, super_tab);
         GS_CUDA_TRY(cudaGetLastError());
-        super_prefix_kernel<<<C.row_tiles / 128, 128, 0, st>>>(sizes, C.row_tiles, super_tab, tile_total);
-        GS_CUDA_TRY(cudaGetLastError());
-        tile_scan_kernel<<<1, 1024, 0, st>>>(sizes, num_tiles, tile_total, tile_start, tile_ranges);
-        GS_CUDA_TRY(cudaGetLastError());
         {
             ListCap cap = {list_cap > 0 ? (uint32_t)list_cap : 0xFFFFFFFFu, nullptr, nullptr, nullptr, 0};
-            if (list_cap > 0 && num_tiles % tiles_x == 0) {
+            // super-chunk prefix, closing chunks (truncated lists), tile scan and the forward's tile order: one launch
+            unsigned int* ticket = (unsigned int*)(wsc + C.close_chunk);
+            int32_t* close_chunk = (int32_t*)(wsc + C.close_chunk + 256);
+            int blocks_x = 0;
+            size_t zero_bytes = 256;
+            const bool closing = list_cap > 0 && num_tiles % tiles_x == 0;
+            if (closing) {
                 const int tiles_y = num_tiles / tiles_x;
-                const int blocks_x = (tiles_x + kCloseBlk - 1) / kCloseBlk, blocks_y = (tiles_y + kCloseBlk - 1) / kCloseBlk;
-                int32_t* close_chunk = (int32_t*)(wsc + C.close_chunk);
-                GS_CUDA_TRY(cudaMemsetAsync(close_chunk, 0, (size_t)blocks_x * blocks_y * sizeof(int32_t), st));
-                close_chunk_kernel<<<(num_tiles + 255) / 256, 256, 0, st>>>(sizes, num_tiles, tiles_x, C.row_tiles, base16,
-                                                                            super_tab, cap.limit, blocks_x, close_chunk);
-                GS_CUDA_TRY(cudaGetLastError());
-                count_launches(1);
+                blocks_x = (tiles_x + kCloseBlk - 1) / kCloseBlk;
+                zero_bytes += (size_t)blocks_x * ((tiles_y + kCloseBlk - 1) / kCloseBlk) * sizeof(int32_t);
+            }
+            GS_CUDA_TRY(cudaMemsetAsync(ticket, 0, zero_bytes, st));
+            tile_tables_kernel<<<(C.row_tiles + kTablesThreads - 1) / kTablesThreads, kTablesThreads, 0, st>>>(
+                sizes, num_tiles, tiles_x, C.row_tiles, base16, super_tab, tile_total, tile_start, tile_ranges, cap.limit, blocks_x,
+                closing ? close_chunk : nullptr, tile_order, ticket);
+            GS_CUDA_TRY(cudaGetLastError());
+            if (closing) {
                 cap.close_chunk = close_chunk;
                 cap.blocks_x = blocks_x;
             }
@@ -939,7 +1095,7 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
                 super_tab, tile_start, depth_keys, entry_ids, entry_keys, cap);
         }
         GS_CUDA_TRY(cudaGetLastError());
-        count_launches(5);
+        count_launches(4);
         return GS_OK;
     }
     const SortLayout L = sort_layout(d, num_tiles);

@@ -135,13 +135,141 @@ peer_allreduce_multimem_kernel(float* mc, int world, int rank, int64_t sum_off4,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA variant (GS_PEER_TMA): the same exchange with the data moved by bulk asynchronous copies instead of per-thread
+// 16-byte loads/stores.  An SM can keep only a few dozen peer requests of <= 128 B in flight, which is what pins the
+// load/store kernel to ~1/3 of the NVLink rate whatever its occupancy (profiles/r1_v5_multigpu.md); one
+// cp.async.bulk moves 8 KB per request, needs no registers for the data in flight and completes on an mbarrier.
+// Per CTA a ring of kTmaStages stages; a stage holds the same chunk of this rank's slice from every peer:
+//   thread 0:    expect_tx + one bulk load per peer  ->  stage, signalled on the stage's mbarrier
+//   all threads: wait, reduce the `world` copies in a fixed order into copy 0 (SUM or MAX), proxy fence, barrier
+//   thread 0:    one bulk store of copy 0 per peer (commit group), wait until the stores have READ the stage, refill it
+// One owner per element and a fixed summation order, as in the load/store kernel: results are bit-identical on all
+// ranks and bit-identical to that kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaThreads = 256;
+constexpr int kTmaStages = 3;
+constexpr int kTmaStageBytes = 64 * 1024;        // world x chunk bytes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tGS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GS_DONE_%=;\n\tbra GS_WAIT_%=;\n\tGS_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int kWorld>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+peer_allreduce_tma_kernel(PeerPtrs peers, int world_rt, int rank, int64_t sum_off4, int64_t sum_n4, int64_t max_off4, int64_t max_n4) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    const int world = kWorld > 0 ? kWorld : world_rt;
+    const int chunk4 = kTmaStageBytes / 16 / world;                    // float4 per peer per stage (multiple of 8 -> 128-byte pieces)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tma_smem);              // kTmaStages mbarriers
+    float4* stages = reinterpret_cast<float4*>(tma_smem + 128);
+    const int tid = threadIdx.x;
+
+    // this rank's slices of the two regions, cut into chunks
+    auto slice = [&](int64_t off4, int64_t n4, int64_t& b, int64_t& e) {
+        const int64_t per = (n4 + world - 1) / world;
+        b = min((int64_t)rank * per, n4);
+        e = min(b + per, n4);
+        b += off4; e += off4;
+    };
+    int64_t sb, se, mb, me;
+    slice(sum_off4, sum_n4, sb, se);
+    slice(max_off4, max_n4, mb, me);
+    const int64_t nc_sum = (se - sb + chunk4 - 1) / chunk4, nc_max = (me - mb + chunk4 - 1) / chunk4;
+    const int64_t total = nc_sum + nc_max;
+    const int64_t mine = total > (int64_t)blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto chunk_of = [&](int64_t j, int64_t& start, int& len, bool& is_max) {
+        const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
+        is_max = t >= nc_sum;
+        const int64_t b = is_max ? mb : sb, e = is_max ? me : se;
+        start = b + (is_max ? t - nc_sum : t) * chunk4;
+        len = (int)min((int64_t)chunk4, e - start);
+    };
+    auto issue = [&](int64_t j) {                                       // thread 0 only
+        int64_t start; int len; bool is_max;
+        chunk_of(j, start, len, is_max);
+        const int s = (int)(j % kTmaStages);
+        mbar_expect_tx(&bars[s], (uint32_t)(world * len * 16));
+        for (int p = 0; p < world; ++p)
+            bulk_g2s(stages + ((int64_t)s * world + p) * chunk4, reinterpret_cast<const float4*>(peers.p[p]) + start, (uint32_t)(len * 16), &bars[s]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int64_t j = 0; j < mine && j < kTmaStages; ++j) issue(j);
+
+    for (int64_t j = 0; j < mine; ++j) {
+        int64_t start; int len; bool is_max;
+        chunk_of(j, start, len, is_max);
+        const int s = (int)(j % kTmaStages);
+        mbar_wait(&bars[s], (uint32_t)((j / kTmaStages) & 1));
+        float4* st = stages + (int64_t)s * world * chunk4;
+        for (int i = tid; i < len; i += kTmaThreads) {
+            float4 acc = st[i];
+#pragma unroll
+            for (int p = 1; p < (kWorld > 0 ? kWorld : kMaxPeers); ++p) {
+                if (p < world) {
+                    const float4 v = st[(int64_t)p * chunk4 + i];
+                    if (is_max) {
+                        acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+                    } else {
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                }
+            }
+            st[i] = acc;
+        }
+        fence_async_smem();                           // generic-proxy writes -> visible to the bulk stores below
+        __syncthreads();
+        if (tid == 0) {
+            for (int p = 0; p < world; ++p)
+                bulk_s2g(reinterpret_cast<float4*>(peers.p[p]) + start, st, (uint32_t)(len * 16));
+            bulk_commit();
+            if (j + kTmaStages < mine) {
+                bulk_wait_read_all();                 // the stores have read the stage: it may be overwritten
+                issue(j + kTmaStages);
+            }
+        }
+    }
+    if (tid == 0) {
+        bulk_wait_all();                              // every store of this CTA is complete before the kernel (and the barrier after it) ends
+        __threadfence_system();
+    }
+}
+
 }  // namespace gs
 
 using namespace gs;
 
 extern "C" int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int32_t world, int32_t rank,
                                  int64_t sum_offset, int64_t sum_count, int64_t max_offset, int64_t max_count,
-                                 void* stream) {
+                                 int32_t flags, void* stream) {
     GS_REQUIRE(peer_ptrs_host != nullptr, "peer_ptrs_host is NULL");
     GS_REQUIRE(world >= 1 && world <= kMaxPeers, "world must be 1..16");
     GS_REQUIRE(rank >= 0 && rank < world, "rank out of range");
@@ -166,6 +294,25 @@ extern "C" int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multic
     if (multicast_ptr != 0) {
         GS_REQUIRE(multicast_ptr % 16 == 0, "multicast address must be 16-byte aligned");
         peer_allreduce_multimem_kernel<<<grid, block, 0, st>>>(reinterpret_cast<float*>(multicast_ptr), world, rank, so, sn, mo, mn);
+        GS_CUDA_TRY(cudaGetLastError());
+        count_launches(1);
+        return GS_OK;
+    }
+    if (flags & GS_PEER_TMA) {
+        const size_t smem = 128 + (size_t)kTmaStages * kTmaStageBytes;
+        const dim3 tgrid((unsigned)sms);
+#define GS_TMA_LAUNCH(W)                                                                                                   \
+    do {                                                                                                                   \
+        GS_CUDA_TRY(cudaFuncSetAttribute(peer_allreduce_tma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        peer_allreduce_tma_kernel<W><<<tgrid, kTmaThreads, smem, st>>>(peers, world, rank, so, sn, mo, mn);                \
+    } while (0)
+        switch (world) {
+            case 2: GS_TMA_LAUNCH(2); break;
+            case 4: GS_TMA_LAUNCH(4); break;
+            case 8: GS_TMA_LAUNCH(8); break;
+            default: GS_TMA_LAUNCH(0); break;
+        }
+#undef GS_TMA_LAUNCH
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
         return GS_OK;

@@ -117,8 +117,10 @@ class FlatGradBuffer:
                 mc = int(handle.multicast_ptr or 0)
             except Exception:
                 mc = 0
+        # GSPLAT_B200_PEER_TMA=1: bulk asynchronous copies (TMA) instead of per-thread loads/stores (GS_PEER_TMA)
+        flags = 1 if os.environ.get("GSPLAT_B200_PEER_TMA", "0") == "1" else 0
         self.peer = {"handle": handle, "rank": int(handle.rank), "world": int(handle.world_size),
-                     "ptrs": (ctypes.c_uint64 * len(ptrs))(*ptrs), "multicast": mc}
+                     "ptrs": (ctypes.c_uint64 * len(ptrs))(*ptrs), "multicast": mc, "flags": flags}
         return t
 
     def install(self, zero: bool = True) -> None:
@@ -146,7 +148,7 @@ class FlatGradBuffer:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.storage.device).cuda_stream)
         h.barrier(channel=0)                 # every rank's buffer is complete (device-side, on this stream)
         _lib.check(_lib.load().gs_peer_allreduce(self.peer["ptrs"], self.peer["multicast"], self.peer["world"], self.peer["rank"],
-                                                 0, self.sum_elems, self.sum_elems, self.max_elems, stream),
+                                                 0, self.sum_elems, self.sum_elems, self.max_elems, self.peer["flags"], stream),
                    "gs_peer_allreduce")
         h.barrier(channel=1)                 # every rank's slice has landed everywhere
 

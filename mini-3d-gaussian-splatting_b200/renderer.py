@@ -279,11 +279,15 @@ class _RasterizeFn(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=_U8, device=dev)
             if cap:
                 flagbuf.zero_()
+            # this frame's list lengths give the forward's tile order: the flat counting sort emits it from the launch
+            # that scans the tiles; the other algorithms need the separate kernel
+            fused_order = prev is None and int(bins.algo) == 1
             with _timed("bin_sort", dev):
                 check(lib.gs_bin_sort(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
                                       ptr(bins.depth_keys), tiles_x, tiles, int(bins.algo), ptr(ws), ws.numel(),
-                                      ptr(entry_ids), ptr(tile_ranges), None, counters_dev, cap, stream), "gs_bin_sort")
-            if prev is None:                      # this frame's list lengths, available as soon as the binning has run
+                                      ptr(entry_ids), ptr(tile_ranges), None, counters_dev, cap,
+                                      ptr(bins.tile_order) if fused_order else None, stream), "gs_bin_sort")
+            if prev is None and not fused_order:
                 check(lib.gs_tile_order(tiles, None, ptr(tile_ranges), ptr(bins.tile_order), stream), "gs_tile_order")
             vis_host = int(bins.num_vis > 0) if counters_dev is None else 0
 

@@ -270,13 +270,20 @@ def test_sort_keys_bit_exact_vs_oracle():
     entry_ids = torch.empty(D, dtype=torch.int32, device="cuda")
     ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device="cuda")
     ekeys = torch.empty(D, dtype=torch.int64, device="cuda")
+    order = torch.full((num_tiles,), -1, dtype=torch.int32, device="cuda")
     for algo in (1, 2, 3):       # flat counting sort, library radix sort, blocked counting sort: identical sequences
         entry_ids.fill_(-1); ekeys.fill_(-1)
         _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
-                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, 0, st), "sort")
+                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, 0, P(order) if algo == 1 else None, st), "sort")
         assert torch.equal(ekeys.cpu(), o["sort_keys"]), algo
         assert torch.equal(entry_ids.cpu().long(), o["sort_ids"]), algo
         util.assert_same_ranges(ranges, o["tile_ranges"])
+    # the tile order the counting sort emits alongside: a permutation of the tiles, longest lists (buckets of 8) first
+    lens = (ranges[:, 1] - ranges[:, 0]).long().cpu()
+    perm = order.long().cpu()
+    assert torch.equal(torch.sort(perm).values, torch.arange(num_tiles))
+    b = (lens[perm] // 8).clamp(max=255)
+    assert bool((b[1:] <= b[:-1]).all())
 
 
 def test_all_invisible_returns_background_once_unclamped_and_zero_grads():

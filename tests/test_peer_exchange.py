@@ -1,6 +1,6 @@
 """GPU, >= 2 devices: the peer-memory gradient exchange (mini-3d-gaussian-splatting_b200/multiview.py FlatGradBuffer.all_reduce,
 csrc/peer.cu) against NCCL, launched through torchrun -- worlds 2 / 4 / 8 (specialised kernels) and 3 (generic kernel), ragged
-slice boundaries, plain peer loads/stores and the NVSwitch multicast variant.  SURVEY 8e: no reference counterpart (the
+slice boundaries; per-thread peer loads/stores, the NVSwitch multicast variant and the TMA (cp.async.bulk) variant.  SURVEY 8e: no reference counterpart (the
 reference is single-device); the acceptance is "reduced buffer == NCCL all_reduce of the same inputs, bit-identical on all ranks".
 The driver's single-GPU tier skips these; bench.py prints the same checks on the real render gradients (`exchange_check`)
 in every N >= 2 line."""
@@ -16,8 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, n, multicast, port):
-    env = dict(os.environ, GSPLAT_B200_MULTICAST=str(int(multicast)), GSPLAT_B200_PEER="1")
+def _run(world, n, mode, port):
+    env = dict(os.environ, GSPLAT_B200_MULTICAST=str(int(mode == "multicast")), GSPLAT_B200_PEER_TMA=str(int(mode == "tma")),
+               GSPLAT_B200_PEER="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "peer_worker.py"), str(n)],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
@@ -27,15 +28,15 @@ def _run(world, n, multicast, port):
     return json.loads(line[0][len("PEER_RESULT "):])
 
 
-@pytest.mark.parametrize("multicast", [0, 1])
+@pytest.mark.parametrize("mode", ["ldst", "multicast", "tma"])      # per-thread loads/stores, NVSwitch multimem, bulk async copies
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_peer_exchange_equals_nccl(world, multicast):
+def test_peer_exchange_equals_nccl(world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
     n = 100003                                    # sum region 1 600 064 floats = 400 016 float4: not divisible by 3 or 8 -> ragged slices
-    res = _run(world, n, multicast, 29600 + 10 * world + multicast)
+    res = _run(world, n, mode, 29600 + 10 * world + ["ldst", "multicast", "tma"].index(mode))
     assert res["world"] == world
-    if multicast and not res["multicast"]:
+    if mode == "multicast" and not res["multicast"]:
         pytest.skip("no NVSwitch multicast address on this box: the multimem variant did not run")
     for rnd in res["rounds"]:
         assert rnd["sum_rel_err_vs_nccl"] < 2e-6, res            # fp32 sums in a different order

@@ -36,7 +36,7 @@ for mode in ("warm", "flushed"):
         ts.append(a.elapsed_time(b) * 1e3)
     res[mode + "_us"] = [round(float(np.median(ts[2:])), 1), round(float(np.min(ts[2:])), 1)]
 up = lambda x: (x + 255) // 256 * 256
-off = 4 * up(n * 4) + up(1024 * 256 * 4) + up(1024 * 256 * 8) + 16384
+off = 6 * up(n * 4) + up(1024 * 256 * 4) + up(1024 * 256 * 8) + 16384
 stamps = ws[off:off + 48 * 8].view(torch.int64).cpu().numpy()
 if stamps[0] > 0:
     names = ["start", "p0 done", "sync"] + [f"pass{p} {x}" for p in range(4) for x in ("A start", "A done", "sync", "scan done", "B done")] + ["end"] + ["-"] * 8 + [f"pass{p} B {x}" for p in range(4) for x in ("ranked", "reordered", "wscanned", "-")]

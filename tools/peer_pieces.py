@@ -14,8 +14,8 @@ m = gb.GaussianModel(device=dev); m.create_from_random(1_000_000, 1.0, seed=0)
 buf = gb.multiview.FlatGradBuffer(m)
 h = buf.peer["handle"]; lib = _lib.load()
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-def kernel(mc):
-    _lib.check(lib.gs_peer_allreduce(buf.peer["ptrs"], mc, world, rank, 0, buf.sum_elems, buf.sum_elems, buf.max_elems, st()), "k")
+def kernel(mc, flags=0):
+    _lib.check(lib.gs_peer_allreduce(buf.peer["ptrs"], mc, world, rank, 0, buf.sum_elems, buf.sum_elems, buf.max_elems, flags, st()), "k")
 def timeit(fn, reps=20):
     for _ in range(3): fn()
     torch.cuda.synchronize(); dist.barrier()
@@ -29,6 +29,7 @@ def timeit(fn, reps=20):
 out = {"world": world}
 out["two_barriers_ms"] = timeit(lambda: (h.barrier(channel=0), h.barrier(channel=1)))
 out["kernel_p2p_ms"] = timeit(lambda: kernel(0))
+out["kernel_tma_ms"] = timeit(lambda: kernel(0, 1))
 if buf.peer["multicast"]:
     out["kernel_multicast_ms"] = timeit(lambda: kernel(buf.peer["multicast"]))
 for mult in (1, 4, 8):
@@ -37,6 +38,9 @@ for mult in (1, 4, 8):
 os.environ["GS_PEER_GRID_MULT"] = "2"
 out["lib"] = os.environ.get("GSPLAT_B200_LIB", "default")
 out["full_ms"] = timeit(buf.all_reduce)
+buf.peer["flags"] = 1
+out["full_tma_ms"] = timeit(buf.all_reduce)
+buf.peer["flags"] = 0
 x = torch.empty(68_000_000 // 4, device=dev); y = torch.empty_like(x)
 out["local_copy_68MB_ms"] = timeit(lambda: y.copy_(x))
 if rank == 0: print(json.dumps(out), flush=True)
