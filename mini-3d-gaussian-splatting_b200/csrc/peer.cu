@@ -94,6 +94,7 @@ peer_allreduce_kernel(PeerPtrs peers, int world, int rank, int64_t sum_off4, int
 // rank's copy (one request instead of one per peer): link traffic per GPU drops from 2*(G-1)/G of the buffer
 // to 2/G of it.  The MAX region holds non-negative floats, whose order is that of their bit patterns, so it is
 // reduced as .max.u32 (multimem has no f32 max).
+template <int kU>
 __global__ void __launch_bounds__(512)
 peer_allreduce_multimem_kernel(float* mc, int world, int rank, int64_t sum_off4, int64_t sum_n4, int64_t max_off4, int64_t max_n4) {
     const int64_t threads = (int64_t)gridDim.x * blockDim.x;
@@ -101,7 +102,7 @@ peer_allreduce_multimem_kernel(float* mc, int world, int rank, int64_t sum_off4,
     {
         const int64_t per = (sum_n4 + world - 1) / world;
         const int64_t begin = (int64_t)rank * per, end = min(begin + per, sum_n4);
-        constexpr int kU = 4;                              // independent reductions in flight per thread
+        // kU independent in-switch reductions in flight per thread (a reduction's latency is the slowest of `world` reads)
         for (int64_t i0 = begin + tid; i0 < end; i0 += threads * kU) {
             float4 v[kU];
 #pragma unroll
@@ -293,7 +294,12 @@ extern "C" int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multic
     const int64_t so = sum_offset / 4, sn = sum_count / 4, mo = max_offset / 4, mn = max_count / 4;
     if (multicast_ptr != 0) {
         GS_REQUIRE(multicast_ptr % 16 == 0, "multicast address must be 16-byte aligned");
-        peer_allreduce_multimem_kernel<<<grid, block, 0, st>>>(reinterpret_cast<float*>(multicast_ptr), world, rank, so, sn, mo, mn);
+        int unroll = 4;
+        if (const char* e = getenv("GS_PEER_MC_UNROLL")) unroll = atoi(e);                  // tuning knob (tools/peer_pieces.py)
+        float* mcp = reinterpret_cast<float*>(multicast_ptr);
+        if (unroll >= 16) peer_allreduce_multimem_kernel<16><<<grid, block, 0, st>>>(mcp, world, rank, so, sn, mo, mn);
+        else if (unroll >= 8) peer_allreduce_multimem_kernel<8><<<grid, block, 0, st>>>(mcp, world, rank, so, sn, mo, mn);
+        else peer_allreduce_multimem_kernel<4><<<grid, block, 0, st>>>(mcp, world, rank, so, sn, mo, mn);
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
         return GS_OK;

@@ -117,8 +117,11 @@ class FlatGradBuffer:
                 mc = int(handle.multicast_ptr or 0)
             except Exception:
                 mc = 0
-        # GSPLAT_B200_PEER_TMA=1: bulk asynchronous copies (TMA) instead of per-thread loads/stores (GS_PEER_TMA)
-        flags = 1 if os.environ.get("GSPLAT_B200_PEER_TMA", "0") == "1" else 0
+        # GS_PEER_TMA: bulk asynchronous copies (TMA) instead of per-thread loads/stores.  Measured on this pool's boxes
+        # (profiles/r2_multigpu.md): identical at 2 GPUs (both sit at the ~315 GB/s per-direction NVLink rate), 10 %
+        # faster at 8 (0.188 vs 0.210 ms) -- default from 4 ranks up; GSPLAT_B200_PEER_TMA=0/1 overrides
+        tma_env = os.environ.get("GSPLAT_B200_PEER_TMA", "")
+        flags = int(tma_env == "1") if tma_env in ("0", "1") else int(len(ptrs) >= 4)
         self.peer = {"handle": handle, "rank": int(handle.rank), "world": int(handle.world_size),
                      "ptrs": (ctypes.c_uint64 * len(ptrs))(*ptrs), "multicast": mc, "flags": flags}
         return t

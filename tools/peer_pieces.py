@@ -30,8 +30,18 @@ out = {"world": world}
 out["two_barriers_ms"] = timeit(lambda: (h.barrier(channel=0), h.barrier(channel=1)))
 out["kernel_p2p_ms"] = timeit(lambda: kernel(0))
 out["kernel_tma_ms"] = timeit(lambda: kernel(0, 1))
-if buf.peer["multicast"]:
-    out["kernel_multicast_ms"] = timeit(lambda: kernel(buf.peer["multicast"]))
+mc_ptr = buf.peer["multicast"]
+if not mc_ptr:
+    try:
+        mc_ptr = int(buf.peer["handle"].multicast_ptr or 0)
+    except Exception:
+        mc_ptr = 0
+if mc_ptr:
+    for unroll in (4, 8, 16):
+        for mult in (2, 4):
+            os.environ["GS_PEER_MC_UNROLL"], os.environ["GS_PEER_GRID_MULT"] = str(unroll), str(mult)
+            out[f"kernel_multicast_u{unroll}_g{mult}_ms"] = timeit(lambda: kernel(mc_ptr))
+    os.environ["GS_PEER_GRID_MULT"] = "2"
 for mult in (1, 4, 8):
     os.environ["GS_PEER_GRID_MULT"] = str(mult)
     out[f"kernel_p2p_grid{mult}_ms"] = timeit(lambda: kernel(0))
