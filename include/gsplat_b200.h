@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 17
+#define GS_ABI_VERSION 18
 
 typedef enum GsStatus {
     GS_OK = 0,
@@ -53,8 +53,9 @@ typedef enum GsStatus {
 #define GS_CAMERA_FLOATS 20
 
 /* Per-splat record consumed by the raster kernels: 12 floats = 3 x float4, 48-byte stride.
- *   {mx, my, c*Q00, c*(Q01+Q10)} {c*Q11, opacity, depth, r} {g, b, regular, 0},  c = -0.5*log2(e):
- * the splat weight exp(-0.5*s) of renderer.py:333-334 is then one exp2 of the quadratic form.
+ *   {mx, my, c*Q00, c*(Q01+Q10)} {c*Q11, opacity, depth, r} {g, b, regular, log2(opacity)},  c = -0.5*log2(e):
+ * the splat weight exp(-0.5*s) of renderer.py:333-334 is then one exp2 of the quadratic form, and for
+ * `regular` records opacity * weight is one exp2 of (quadratic form + log2 opacity).
  * `regular` (1.0 / 0.0) marks splats with opacity in [0,1] and a positive-definite, well-conditioned
  * conic, for which the two clamps of renderer.py:335,339 are identities: batches of such entries take
  * a shorter instruction sequence in gs_raster_fwd / gs_raster_bwd (same results; a record with

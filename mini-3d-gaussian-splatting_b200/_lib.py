@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 LIB_NAME = "libgsplat_b200.so"
 # GSPLAT_B200_LIB points at an alternative build of the same ABI (kernel-variant experiments, tools/)
 LIB_PATH = os.environ.get("GSPLAT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)

@@ -342,7 +342,10 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
     const float det_s = s00 * s11 - 0.25f * s01 * s01, tr_s = s00 + s11;
     const bool regular = (op >= 0.f) && (op <= 1.f) && (s00 < 0.f) && (s11 < 0.f) && (det_s >= 1e-5f * tr_s * tr_s) &&
                          (tr_s > -1e30f);
-    rec[i * 3 + 2] = make_float4(cg, cb, regular ? 1.f : 0.f, 0.f);
+    // log2(opacity): the fast path folds the opacity into the exponent, a = 2^(c*s + log2 opacity); -inf for the opacities the
+    // compositing kernels stage as zero (<= 1e-30, renderer.py:340 skips a <= 0)
+    const float lop = (op > 1e-30f) ? log2f(op) : __int_as_float(0xff800000);
+    rec[i * 3 + 2] = make_float4(cg, cb, regular ? 1.f : 0.f, lop);
 }
 
 // Backward (derived from the forward above).

@@ -47,6 +47,9 @@ constexpr float kTermA = 0.995f;       // renderer.py:352
 constexpr float kMinW = 1e-5f;         // renderer.py:336
 constexpr float kLn2 = 0.69314718056f;
 constexpr float kNegHalfLog2e = -0.72134752044448170f;
+// log2 of the fp32 value of kMinW: on the fast path the opacity is folded into the exponent (a = 2^(s' + log2 opacity)),
+// so the reference's `w < 1e-5` rule is tested on the exponent: s' + log2 opacity >= log2(1e-5) + log2 opacity.
+constexpr float kLog2MinW = -16.609640510882354f;
 // Opacities at or below this are skipped as a whole (warp-uniform).  The reference skips a <= 0
 // (renderer.py:340); for 0 < opacity <= 1e-30 it would add < 1e-30 to every accumulator.
 constexpr float kTinyOpacity = 1e-30f;
@@ -94,8 +97,8 @@ template <bool kPk> __device__ __forceinline__ float2 mul2s(float2 a, float2 b) 
 
 // Per-entry values shared by a lane's 8 pixels, pre-broadcast into pairs.
 struct EntryRow {
-    float2 neg_mx, q00, qsdy, q11dy2;
-    float op;
+    float2 neg_mx, q00, qsdy, q11dy2;      // fast path: q11dy2 also carries log2(opacity)
+    float op;                              // general path: opacity; fast path: log2(kMinW) + log2(opacity)
 };
 
 // renderer.py:330-346 for one pixel pair.  `A >= kTermA` encodes "this pixel has terminated (or
@@ -123,6 +126,14 @@ __device__ __forceinline__ float live_weight(float A, float e) {
         : "=f"(wm) : "f"(A), "f"(kTermA), "f"(e), "f"(kMinW));
     return wm;
 }
+// fast path: am = (A < kTermA && sp >= thr) ? a : 0 with a = 2^sp = opacity * w and thr = log2(kMinW) + log2(opacity);
+// the compares do not wait for the MUFU result
+__device__ __forceinline__ float live_alpha(float A, float sp, float thr, float a) {
+    float am;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\tsetp.ge.and.f32 p, %3, %4, p;\n\tselp.f32 %0, %5, 0f00000000, p;\n\t}"
+        : "=f"(am) : "f"(A), "f"(kTermA), "f"(sp), "f"(thr), "f"(a));
+    return am;
+}
 __device__ __forceinline__ float live_select(float A, float w, float c) {
     float r;
     asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\tsetp.ge.and.f32 p, %3, %4, p;\n\tselp.f32 %0, %5, 0f00000000, p;\n\t}"
@@ -138,12 +149,14 @@ __device__ __forceinline__ void eval_pair(float2 fpx, const EntryRow& r, float2 
     ev.e = make_float2(ex2_approx(sp.x), ex2_approx(sp.y));
     ev.T = fma2s<kPk>(A, bc2(-1.0f), bc2(1.0f));                              // 1 - A, one rounding
     if (kFast) {
-        ev.w = make_float2(live_weight(A.x, ev.e.x), live_weight(A.y, ev.e.y));
-        ev.u = mul2s<kPk>(bc2(r.op), ev.w);
-        ev.a = ev.u;
+        // the exponent already holds log2(opacity): e = opacity * w, one multiply less per pixel.  `w`, `u` and `a` all
+        // name that product here; the backward divides the opacity out once per entry.
+        ev.a = make_float2(live_alpha(A.x, sp.x, r.op, ev.e.x), live_alpha(A.y, sp.y, r.op, ev.e.y));
+        ev.w = ev.a;
+        ev.u = ev.a;
         ev.contrib = mul2s<kPk>(ev.T, ev.a);
-        ev.act0 = ev.w.x > 0.f;
-        ev.act1 = ev.w.y > 0.f;
+        ev.act0 = ev.a.x > 0.f;
+        ev.act1 = ev.a.y > 0.f;
     } else {
         ev.w = make_float2(fminf(ev.e.x, 1.0f), fminf(ev.e.y, 1.0f));      // clamp(exp(.), 0, 1); exp >= 0
         ev.u = mul2s<kPk>(bc2(r.op), ev.w);
@@ -158,24 +171,35 @@ __device__ __forceinline__ void eval_pair(float2 fpx, const EntryRow& r, float2 
     }
 }
 
-__device__ __forceinline__ void load_entry_row(const float4& r0, const float4& r1, float fpy, EntryRow& row, float& dy) {
+// `lop` = log2(opacity) from the record (-inf for an entry staged with opacity 0); only the fast path uses it.
+template <bool kFast>
+__device__ __forceinline__ void load_entry_row(const float4& r0, const float4& r1, float lop, float fpy, EntryRow& row, float& dy) {
     dy = fpy - r0.y;
     row.neg_mx = bc2(-r0.x);
     row.q00 = bc2(r0.z);
     row.qsdy = bc2(r0.w * dy);
-    row.q11dy2 = bc2(r1.x * dy * dy);
-    row.op = r1.y;
+    if (kFast) {
+        row.q11dy2 = bc2(r1.x * dy * dy + lop);
+        row.op = kLog2MinW + lop;
+    } else {
+        row.q11dy2 = bc2(r1.x * dy * dy);
+        row.op = r1.y;
+    }
 }
 
 // Stages one list entry's record into shared memory; returns whether it is "regular" (fast path).
 __device__ __forceinline__ bool stage_entry(const float4* __restrict__ rec, int id, float4* dst) {
     float4 q1 = __ldg(&rec[(int64_t)id * 3 + 1]);
     const float4 q2 = __ldg(&rec[(int64_t)id * 3 + 2]);
-    q1.y = (q1.y > kTinyOpacity) ? q1.y : 0.f;      // opacity 0 => a = 0 => the entry adds exact zeros
+    const bool tiny = !(q1.y > kTinyOpacity);
+    const bool regular = q2.z != 0.f;
+    q1.y = tiny ? 0.f : q1.y;                        // opacity 0 => a = 0 => the entry adds exact zeros
     dst[0] = __ldg(&rec[(int64_t)id * 3 + 0]);
     dst[1] = q1;
-    dst[2] = q2;
-    return q2.z != 0.f;
+    // shared-memory copy: {g, b, 1/opacity, log2 opacity} -- the flag has been read, its slot carries the reciprocal
+    // the backward needs once per entry (dL/d opacity = sum(dL/da * a) / opacity)
+    dst[2] = make_float4(q2.x, q2.y, tiny ? 0.f : __frcp_rn(q1.y), tiny ? __int_as_float(0xff800000) : q2.w);
+    return regular;
 }
 
 // ---- asynchronous staging (GS_PREFETCH=1, off by default): the records of batch b+1 travel global -> shared
@@ -200,8 +224,11 @@ __device__ __forceinline__ void stage_entry_async(const float4* __restrict__ rec
 // after the copy has landed: the lane that staged an entry applies the tiny-opacity rule and reads its flag
 __device__ __forceinline__ bool fixup_entry(float4* dst) {
     const float op = dst[1].y;
-    if (!(op > kTinyOpacity)) dst[1].y = 0.f;
-    return dst[2].z != 0.f;
+    const bool tiny = !(op > kTinyOpacity);
+    const bool regular = dst[2].z != 0.f;
+    if (tiny) { dst[1].y = 0.f; dst[2].w = __int_as_float(0xff800000); }
+    dst[2].z = tiny ? 0.f : __frcp_rn(op);
+    return regular;
 }
 
 // One batch of the forward walk (cnt staged entries); returns how many of them were composited.  Every
@@ -226,10 +253,10 @@ __device__ __forceinline__ int fwd_batch(const float4* srec, int cnt, int first_
         for (int j = j0; j < jn; ++j) {
             const float4 r0 = srec[j * 3 + 0];          // mx, my, q00', qs'
             const float4 r1 = srec[j * 3 + 1];          // q11', opacity (0 if tiny), z, r
-            const float2 r2 = *reinterpret_cast<const float2*>(&srec[j * 3 + 2]);   // g, b
+            const float4 r2 = srec[j * 3 + 2];          // g, b, 1/opacity, log2 opacity
             EntryRow row;
             float dy;
-            load_entry_row(r0, r1, fpy, row, dy);
+            load_entry_row<kFast>(r0, r1, r2.w, fpy, row, dy);
             const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
 #pragma unroll
             for (int p = 0; p < kPairs; ++p) {
@@ -427,12 +454,14 @@ __device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id
     const float s = acc.x + acc.y;
     const float s2 = __shfl_down_sync(0xffffffffu, s, 10);
     const float s3 = __shfl_down_sync(0xffffffffu, s, 20);
-    if (lane < kRedVals) {
-        const float total = s + s2 + s3;
-        float* dst = out.base + (int64_t)id * out.stride;
-        atomicAdd(dst, total);
-        if (lane == 3) atomicAdd(dst + 1, total);      // Q01 and Q10 enter s symmetrically
-    }
+    // lanes 0..9 hold the ten totals; lane 10 takes a copy of Q01's for Q10 (both enter s symmetrically), so that ONE
+    // reduction instruction serves all eleven addresses.  32-bit element offset: id * stride < 2^31 for every array the
+    // ABI accepts.
+    float total = s + s2 + s3;
+    const float q01 = __shfl_sync(0xffffffffu, total, 3);
+    total = (lane == kRedVals) ? q01 : total;
+    float* dst = out.base + (unsigned)id * (unsigned)out.stride;
+    if (lane <= kRedVals) atomicAdd(dst, total);
 }
 
 // Per-lane partial sums of one list entry over the lane's pixels.
@@ -441,7 +470,8 @@ struct BwdAcc {
 };
 
 // Backward arithmetic of one list entry for ONE pixel pair (kPk: packed or scalar FP32 instructions, same results).
-template <bool kFast, bool kPk>
+// kFirst: the lane's first pair of this entry initialises the partial sums instead of adding to zeros.
+template <bool kFast, bool kPk, bool kFirst>
 __device__ __forceinline__ void bwd_pair(float2 fpx, const EntryRow& row, float2& A, float2& R, float2 gCr, float2 gCg, float2 gCb,
                                          float2 gDs, float2 gA, float2 cr, float2 cg, float2 cb, float2 z, BwdAcc& acc) {
     PairEval ev;
@@ -458,31 +488,51 @@ __device__ __forceinline__ void bwd_pair(float2 fpx, const EntryRow& row, float2
     nsuf.y = (A.y >= kTermA) ? 0.f : nsuf.y;
     float2 g_a = fma2s<kPk>(ev.T, v, nsuf);
     if (kFast) {
-        // ev.w is already zero where the reference skips the splat, and g_a only ever appears multiplied
-        // by it, so no further masking (both clamps are identities on this path).  dL/ds' = ln2*op*(w*g_a):
-        // the constant factor is applied once per entry, which also makes sum(h) the opacity sum itself.
-        const float2 gw = mul2s<kPk>(g_a, ev.w);
-        const float2 gwdx = mul2s<kPk>(gw, ev.dx);
-        acc.s_op = add2s<kPk>(acc.s_op, gw);
-        acc.s_x = add2s<kPk>(acc.s_x, gwdx);
-        acc.s_xx = fma2s<kPk>(gwdx, ev.dx, acc.s_xx);
+        // ev.a = opacity * w is already zero where the reference skips the splat, and g_a only ever appears multiplied
+        // by it, so no further masking (both clamps are identities on this path).  With s'' = s' + log2(opacity) and
+        // a = 2^s'':  dL/ds' = ln2 * (a * g_a), and dL/d opacity = sum(w * g_a) = sum(a * g_a) / opacity: the constant
+        // factors are applied once per entry.
+        const float2 ga = mul2s<kPk>(g_a, ev.a);
+        const float2 gadx = mul2s<kPk>(ga, ev.dx);
+        if (kFirst) {
+            acc.s_op = ga;
+            acc.s_x = gadx;
+            acc.s_xx = mul2s<kPk>(gadx, ev.dx);
+        } else {
+            acc.s_op = add2s<kPk>(acc.s_op, ga);
+            acc.s_x = add2s<kPk>(acc.s_x, gadx);
+            acc.s_xx = fma2s<kPk>(gadx, ev.dx, acc.s_xx);
+        }
     } else {
         // a = clamp(op*w, 0, 1), w = clamp(exp(-s/2), 0, 1): closed-interval pass-through
         g_a.x = (ev.act0 && ev.u.x <= 1.f) ? g_a.x : 0.f;
         g_a.y = (ev.act1 && ev.u.y <= 1.f) ? g_a.y : 0.f;
         float2 h = mul2s<kPk>(ev.w, g_a);
-        acc.s_op = add2s<kPk>(acc.s_op, h);
+        acc.s_op = kFirst ? h : add2s<kPk>(acc.s_op, h);
         h.x = (ev.e.x <= 1.f) ? h.x : 0.f;
         h.y = (ev.e.y <= 1.f) ? h.y : 0.f;
         const float2 hdx = mul2s<kPk>(h, ev.dx);
-        acc.s_h = add2s<kPk>(acc.s_h, h);
-        acc.s_x = add2s<kPk>(acc.s_x, hdx);
-        acc.s_xx = fma2s<kPk>(hdx, ev.dx, acc.s_xx);
+        if (kFirst) {
+            acc.s_h = h;
+            acc.s_x = hdx;
+            acc.s_xx = mul2s<kPk>(hdx, ev.dx);
+        } else {
+            acc.s_h = add2s<kPk>(acc.s_h, h);
+            acc.s_x = add2s<kPk>(acc.s_x, hdx);
+            acc.s_xx = fma2s<kPk>(hdx, ev.dx, acc.s_xx);
+        }
     }
-    acc.s_cr = fma2s<kPk>(ev.contrib, gCr, acc.s_cr);
-    acc.s_cg = fma2s<kPk>(ev.contrib, gCg, acc.s_cg);
-    acc.s_cb = fma2s<kPk>(ev.contrib, gCb, acc.s_cb);
-    acc.s_z = fma2s<kPk>(ev.contrib, gDs, acc.s_z);
+    if (kFirst) {
+        acc.s_cr = mul2s<kPk>(ev.contrib, gCr);
+        acc.s_cg = mul2s<kPk>(ev.contrib, gCg);
+        acc.s_cb = mul2s<kPk>(ev.contrib, gCb);
+        acc.s_z = mul2s<kPk>(ev.contrib, gDs);
+    } else {
+        acc.s_cr = fma2s<kPk>(ev.contrib, gCr, acc.s_cr);
+        acc.s_cg = fma2s<kPk>(ev.contrib, gCg, acc.s_cg);
+        acc.s_cb = fma2s<kPk>(ev.contrib, gCb, acc.s_cb);
+        acc.s_z = fma2s<kPk>(ev.contrib, gDs, acc.s_z);
+    }
 }
 
 // Arithmetic of ONE list entry for this lane's 8 pixels; leaves the 10 per-lane partial sums in
@@ -494,28 +544,30 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
                                           const float2 (&gDs)[kPairs], const float2 (&gA)[kPairs], float* rb) {
     const float4 r0 = srec_j[0];
     const float4 r1 = srec_j[1];
-    const float2 r2 = *reinterpret_cast<const float2*>(&srec_j[2]);
+    const float4 r2 = srec_j[2];                        // g, b, 1/opacity, log2 opacity
     const float op = r1.y;
     EntryRow row;
     float dy;
-    load_entry_row(r0, r1, fpy, row, dy);
+    load_entry_row<kFast>(r0, r1, r2.w, fpy, row, dy);
     const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
     BwdAcc acc;
-    acc.s_h = acc.s_x = acc.s_xx = acc.s_op = acc.s_z = acc.s_cr = acc.s_cg = acc.s_cb = bc2(0.f);
+    acc.s_h = bc2(0.f);
+    bwd_pair<kFast, (kPairs > GS_BWD_SCALAR_PAIRS), true>(fpx[0], row, A[0], R[0], gCr[0], gCg[0], gCb[0], gDs[0], gA[0], cr, cg, cb, z, acc);
 #pragma unroll
-    for (int p = 0; p < kPairs; ++p) {
+    for (int p = 1; p < kPairs; ++p) {
         if (p < kPairs - GS_BWD_SCALAR_PAIRS)
-            bwd_pair<kFast, true>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
+            bwd_pair<kFast, true, false>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
         else
-            bwd_pair<kFast, false>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
+            bwd_pair<kFast, false, false>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
     }
     const float2 s_h = acc.s_h, s_x = acc.s_x, s_xx = acc.s_xx, s_op = acc.s_op, s_z = acc.s_z;
     const float2 s_cr = acc.s_cr, s_cg = acc.s_cg, s_cb = acc.s_cb;
     // an entry staged with opacity 0 (<= kTinyOpacity, or negative) is one the reference skips (a <= 0):
     // every sum below is then an exact zero except the opacity one, which is forced to zero
+    // (fast path: the pixel sums hold a * dL/da with a = opacity * w, so the opacity is divided out here and dL/ds' needs ln2 only)
     const float Sop_all = s_op.x + s_op.y;
-    const float Sop = (op > 0.f) ? Sop_all : 0.f;
-    const float hs = kLn2 * op;                         // dL/ds' = ln2 * op * w * dL/da
+    const float Sop = (op > 0.f) ? (kFast ? Sop_all * srec_j[2].z : Sop_all) : 0.f;     // 1/opacity: re-read, not kept live
+    const float hs = kFast ? kLn2 : kLn2 * op;          // dL/ds' = ln2 * op * w * dL/da
     const float Sh = hs * (kFast ? Sop_all : (s_h.x + s_h.y)), Sx = hs * (s_x.x + s_x.y), Sxx = hs * (s_xx.x + s_xx.y);
     const float dySh = dy * Sh;
     rb[0 * kRedStride + lane] = -fmaf(2.f * r0.z, Sx, r0.w * dySh);             // g_mx
@@ -587,7 +639,8 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         case 6: out_base = g_depths; out_stride = 1; break;
         case 7: out_base = g_colors; out_stride = 3; break;
         case 8: out_base = g_colors + 1; out_stride = 3; break;
-        default: out_base = g_colors + 2; out_stride = 3; break;
+        case 9: out_base = g_colors + 2; out_stride = 3; break;
+        default: out_base = g_conics + 2; out_stride = 4; break;  // lane 10: Q10 (a copy of Q01's sum); lanes > 10 never store
     }
     // lanes 0..29: value red_v, third red_g of the 32 partials (12 + 12 + 8)
     const int red_v = lane % kRedVals, red_g = lane / kRedVals;
@@ -671,7 +724,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
             sid[buf][lane] = first_id;
             mine[0] = make_float4(1.0e6f, 0.f, -1.f, 0.f);
             mine[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            mine[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+            mine[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
@@ -700,7 +753,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
             sid[0][lane] = entry_ids[base];
             srec[0][lane * 3 + 0] = make_float4(1.0e6f, 0.f, -1.f, 0.f);
             srec[0][lane * 3 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            srec[0][lane * 3 + 2] = make_float4(0.f, 0.f, 1.f, 0.f);
+            srec[0][lane * 3 + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
