@@ -12,7 +12,7 @@ BUILDDIR  := build
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
              -Xcompiler -fPIC -DGS_BUILT_FOR_SM=100 \
              --expt-relaxed-constexpr
-CU_SRCS   := $(CSRC)/abi.cu $(CSRC)/project.cu $(CSRC)/binsort.cu $(CSRC)/depthsort.cu $(CSRC)/raster.cu $(CSRC)/peer.cu $(CSRC)/densify.cu
+CU_SRCS   := $(CSRC)/abi.cu $(CSRC)/project.cu $(CSRC)/binsort.cu $(CSRC)/depthsort.cu $(CSRC)/raster.cu $(CSRC)/peer.cu $(CSRC)/densify.cu $(CSRC)/loss.cu
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(BUILDDIR)/%.o,$(CU_SRCS))
 
 all: $(LIBDIR)/libgsplat_b200.so oracle
@@ -39,5 +39,5 @@ clean:
 # kernel-variant experiments: make variant NAME=fwd24 DEFS="-DGS_FWD_MINB=24"  ->  build/variants/libgsplat_b200_fwd24.so
 variant:
 	@mkdir -p build/variants/$(NAME)
-	for f in abi project binsort depthsort raster peer densify; do $(NVCC) $(NVCCFLAGS) $(DEFS) -c $(CSRC)/$$f.cu -o build/variants/$(NAME)/$$f.o || exit 1; done
+	for f in abi project binsort depthsort raster peer densify loss; do $(NVCC) $(NVCCFLAGS) $(DEFS) -c $(CSRC)/$$f.cu -o build/variants/$(NAME)/$$f.o || exit 1; done
 	$(NVCC) -shared -o build/variants/libgsplat_b200_$(NAME).so build/variants/$(NAME)/*.o -cudart static

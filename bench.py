@@ -183,6 +183,7 @@ def main():
     from importlib import import_module
     mv = import_module("mini-3d-gaussian-splatting_b200.multiview")
     rmod = import_module("mini-3d-gaussian-splatting_b200.renderer")
+    fused_losses = import_module("mini-3d-gaussian-splatting_b200.losses")
     lib = import_module("mini-3d-gaussian-splatting_b200._lib").load()
     from oracle import splat_oracle as so   # only for the seeded loss weights shared with the tests / CPU arm
 
@@ -204,13 +205,15 @@ def main():
     cam = gb.Camera.look_at_origin_c0(WIDTH, HEIGHT) if world == 1 else gb.Camera.orbit(rank, world, WIDTH, HEIGHT)
     w_host = [t.pin_memory() for t in so.loss_weights(HEIGHT, WIDTH)]
     w_dev = [t.to(dev) for t in w_host]
+    w_dev[2] = w_dev[2] * 0.1                                         # the loss's 0.1 folded into the depth weights
     buf = mv.FlatGradBuffer(model)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def loss_fn(out, w):
-        # SURVEY 8d loss  sum(w_img*image) + sum(w_a*alpha) + 0.1*sum(w_d*depth), written as three dot products
-        return (torch.dot(w[0].view(-1), out["image"].view(-1)) + torch.dot(w[1].view(-1), out["alpha"].view(-1))
-                + 0.1 * torch.dot(w[2].view(-1), out["depth"].view(-1)))
+        # SURVEY 8d loss  sum(w_img*image) + sum(w_a*alpha) + 0.1*sum(w_d*depth)  (w[2] already carries the 0.1): one fused,
+        # deterministic reduction over the five planes (gs_weighted_sum); its gradient is the weights themselves, so the
+        # backward pass of the loss launches nothing
+        return fused_losses.weighted_sum_loss([out["image"], out["alpha"], out["depth"]], w, grads=w)
 
     def step_device():
         res = mv.multiview_step(model, rd, [cam], settings, lambda out, vid: loss_fn(out, w_dev), buffer=buf, reduce=world > 1)
@@ -228,6 +231,7 @@ def main():
         with torch.cuda.stream(copy_stream):
             for s_, h_ in zip(stage[slot], w_host):
                 s_.copy_(h_, non_blocking=True)
+            stage[slot][2].mul_(0.1)                             # on the copy stream, off the step's critical path
             uploaded[slot].record(copy_stream)
 
     loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -471,7 +475,8 @@ def main():
                        "l2": "flushed before every timed step (256 MiB memset); per-step working set > L2",
                        "renderer": {"binning": "flat counting sort, optimistic sizes, tile lists truncated to their first "
                                                f"{rd.list_cap} entries with a completion path (result identical to complete lists)",
-                                    "tile_order": f"longest first (forward: {rd.fwd_tile_order}; backward: exact work)"},
+                                    "tile_order": f"longest first (forward: {rd.fwd_tile_order}" + (" = this camera's exact work at its previous visit" if rd.fwd_tile_order == "camera" else "") + "; backward: exact work)",
+                                    "loss": "fused weighted sum over the five planes (gs_weighted_sum), gradient = the weights"},
                        "parallelism": (f"view-sharded dp{world}, replicated Gaussians, gradient/statistics exchange of 17N floats: "
                                        + ("one peer-memory kernel per rank over NVLink (gs_peer_allreduce)" if buf.peer is not None
                                           else f"NCCL all_reduce (peer path unavailable: {buf.peer_error})")) if world > 1 else "single GPU"},

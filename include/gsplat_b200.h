@@ -179,7 +179,9 @@ int gs_project_bwd(int64_t n,
  *          for parity checks against the reference order;
  *          tile_order [num_tiles] int32 (optional, flat counting sort only; ignored by the other algorithms): the tiles
  *          sorted by decreasing list length (buckets of 8 entries) -- what gs_tile_order(tile_ranges) would give, produced
- *          by the same launch that scans the tiles.
+ *          by the same launch that scans the tiles;
+ *          flag_count (optional, one int32): set to zero -- the counter of tiles whose stored prefix is too short, which the
+ *          compositing pass enqueued behind this call raises (truncated lists, see gs_bin_complete).
  * ------------------------------------------------------------------------------------- */
 #define GS_BIN_AUTO 0
 #define GS_BIN_COUNTING 1
@@ -201,7 +203,7 @@ int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d,
                 void* workspace, int64_t workspace_bytes,
                 int32_t* entry_ids, int32_t* tile_ranges, uint64_t* entry_keys,
                 const int64_t* counters_dev, int32_t list_cap,
-                int32_t* tile_order, void* stream);
+                int32_t* tile_order, int32_t* flag_count, void* stream);
 
 /* Truncated tile lists (flat counting sort only).  With list_cap > 0 gs_bin_sort stores only the first list_cap
  * entries of every tile's list (tile_ranges still describe the complete lists); gs_raster_fwd, given the same
@@ -257,12 +259,14 @@ int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, const int32_t
  * g_depths [n], g_colors [n,3], g_opacities [n].
  * tile_order_scratch (optional, [num_tiles] int32): when given, the tiles are first bucketed by their exact
  * work (tile_consumed, heaviest first) and taken in that order -- the grid is only a few waves of one-warp
- * CTAs and the tiles' work varies widely, so the natural order leaves full-size tiles in the last wave. */
+ * CTAs and the tiles' work varies widely, so the natural order leaves full-size tiles in the last wave.
+ * tile_order_ready != 0: tile_order_scratch already holds that order (gs_tile_order(tile_consumed), e.g. computed on
+ * another stream while the loss was evaluated) and is only read. */
 int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size,
                   const int32_t* entry_ids, const int32_t* tile_ranges,
                   const float* splat_rec, const float* bg,
                   const float* alpha, const float* pix_state,
-                  const int32_t* tile_consumed, int32_t* tile_order_scratch,
+                  const int32_t* tile_consumed, int32_t* tile_order_scratch, int32_t tile_order_ready,
                   const float* g_image, const float* g_alpha, const float* g_depth,
                   float* g_means2d, float* g_conics, float* g_depths,
                   float* g_colors, float* g_opacities,
@@ -318,6 +322,26 @@ int gs_densify_apply(int64_t n, const void* workspace, int64_t kept, int64_t clo
                      const float* scaling_log, const float* rotation, const float* opacity, const float* noise,
                      float* o_xyz, float* o_features_dc, float* o_features_rest, float* o_scaling_log,
                      float* o_rotation, float* o_opacity, int32_t* src_row, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Loss heads fused into one pass over the rendered planes (the caller of the render path: the reference's
+ * train step computes l1_loss(image, target) = |a - b|.mean() with torch ops, src/utils/loss.py, optimizer.py:137-139).
+ *
+ * Both entry points reduce deterministically (fixed slices, fixed order) into `out` (device, one float) and need a
+ * workspace of gs_loss_workspace_bytes() that the caller zero-fills ONCE (the kernels leave it zeroed again).
+ *
+ * gs_weighted_sum: out = sum_k coeff[k] * dot(x[k], w[k]) over num_terms <= 4 pairs of device arrays of n[k] floats
+ *   (x, w, n, coeff are HOST arrays of num_terms entries).  Its gradient w.r.t. x[k] is coeff[k] * w[k]: no kernel.
+ * gs_l1_loss: out = mean|x - target| over n floats; when `grad` is given it receives
+ *   d(grad_scale * out)/dx = grad_scale * sign(x - target) / n in the same pass (sign(0) = 0, as torch).
+ * ------------------------------------------------------------------------------------- */
+int64_t gs_loss_workspace_bytes(void);
+
+int gs_weighted_sum(int32_t num_terms, const float* const* x, const float* const* w, const int64_t* n,
+                    const float* coeff, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+int gs_l1_loss(const float* x, const float* target, int64_t n, float grad_scale, float* grad, float* out,
+               void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

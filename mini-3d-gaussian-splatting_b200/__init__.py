@@ -8,6 +8,6 @@ from .renderer import GaussianRenderer, RenderSettings  # noqa: F401
 from .scene import Camera, GaussianModel  # noqa: F401
 
 __all__ = ["GaussianRenderer", "RenderSettings", "GaussianModel", "Camera"]
-from . import multiview, training  # noqa: F401,E402
+from . import losses, multiview, training  # noqa: F401,E402
 from .training import DensityController, GaussianOptimizer, LearningRateScheduler, TrainingConfig, train_step  # noqa: F401,E402
 from .io_utils import CameraUtils, IOUtils  # noqa: F401,E402

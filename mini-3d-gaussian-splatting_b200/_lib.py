@@ -35,15 +35,18 @@ SIGNATURES = {
     "gs_bin_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
     "gs_bin_prepare": (c_int32, [c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
     "gs_bin_sort": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,
-                               _P, c_int64, _P, _P, _P, _P, c_int32, _P, _P]),
+                               _P, c_int64, _P, _P, _P, _P, c_int32, _P, _P, _P]),
     "gs_bin_complete": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, c_int32, c_int32, _P, c_int64,
                                    c_int32, _P, _P, _P, _P, _P]),
     "gs_raster_fwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P,
                                  c_int32, _P, _P, c_int32,
                                  _P, _P, _P, _P, _P, _P, _P]),
-    "gs_raster_bwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P,
+    "gs_raster_bwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_int32,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gs_tile_order": (c_int32, [c_int32, _P, _P, _P, _P]),
+    "gs_loss_workspace_bytes": (c_int64, []),
+    "gs_weighted_sum": (c_int32, [c_int32, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "gs_l1_loss": (c_int32, [_P, _P, c_int64, c_float, _P, _P, _P, c_int64, _P]),
 }
 
 

@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(kTablesThreads)
 tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, const uint16_t* __restrict__ base16,
                    uint32_t* __restrict__ super_tab, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ tile_start,
                    int32_t* __restrict__ ranges, uint32_t limit, int blocks_x, int32_t* __restrict__ close_chunk,
-                   int32_t* __restrict__ tile_order, unsigned int* __restrict__ done_counter) {
+                   int32_t* __restrict__ tile_order, unsigned int* __restrict__ done_counter, int32_t* __restrict__ flag_count) {
+    // truncated lists: this frame's count of tiles that need more than their stored prefix starts at zero (the
+    // compositing pass that raises it is enqueued behind this launch)
+    if (flag_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0;
     __shared__ int s_cnt[kOrderBuckets2];
     __shared__ int s_off[kOrderBuckets2];
     __shared__ bool s_last;
@@ -961,7 +964,7 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
                            const uint16_t* tile_rect, const uint32_t* depth_keys, int32_t tiles_x, int32_t num_tiles,
                            int32_t algo, void* workspace, int64_t workspace_bytes, int32_t* entry_ids,
                            int32_t* tile_ranges, uint64_t* entry_keys, const int64_t* counters_dev, int32_t list_cap,
-                           int32_t* tile_order, void* stream) {
+                           int32_t* tile_order, int32_t* flag_count, void* stream) {
     GS_REQUIRE(n >= 0 && num_sorted >= 0 && num_sorted <= n && d >= 0, "bad sizes");
     GS_REQUIRE(num_tiles > 0 && tiles_x > 0, "bad tile grid");
     GS_REQUIRE(tile_ranges != nullptr, "tile_ranges is NULL");
@@ -971,6 +974,9 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     GS_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st));
     const bool nothing = (counters_dev == nullptr && (d == 0 || num_sorted == 0)) ||
                          (counters_dev != nullptr && (d == 0 || n == 0));      // no pairs / no capacity: nothing can be written
+    const bool counting_path = algo == GS_BIN_COUNTING || (algo == GS_BIN_AUTO && num_tiles <= kMaxCountingTiles);
+    // flag_count (truncated lists): zeroed by the flat counting sort's tile-table launch; every other way out zeroes it here
+    if (flag_count != nullptr && (nothing || !counting_path)) GS_CUDA_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
     if (nothing) {
         if (tile_order != nullptr) {                    // all lists are empty: any permutation is the longest-first order
             identity_order_kernel<<<(num_tiles + 255) / 256, 256, 0, st>>>(num_tiles, tile_order);
@@ -1083,7 +1089,7 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
             GS_CUDA_TRY(cudaMemsetAsync(ticket, 0, zero_bytes, st));
             tile_tables_kernel<<<(C.row_tiles + kTablesThreads - 1) / kTablesThreads, kTablesThreads, 0, st>>>(
                 sizes, num_tiles, tiles_x, C.row_tiles, base16, super_tab, tile_total, tile_start, tile_ranges, cap.limit, blocks_x,
-                closing ? close_chunk : nullptr, tile_order, ticket);
+                closing ? close_chunk : nullptr, tile_order, ticket, flag_count);
             GS_CUDA_TRY(cudaGetLastError());
             if (closing) {
                 cap.close_chunk = close_chunk;

@@ -36,10 +36,14 @@ namespace gs {
 #ifndef GS_BWD_MINB
 #define GS_BWD_MINB 16
 #endif
+#ifndef GS_RASTER_WARPS
+#define GS_RASTER_WARPS 1              // tiles (= warps) per CTA; consecutive slots of the launch order, i.e. tiles of similar work
+#endif
 #ifndef GS_BWD_GROUP
 #define GS_BWD_GROUP 2                 // list entries whose arithmetic runs between two warp barriers (backward)
 #endif
 
+constexpr int kWarpsPerCta = GS_RASTER_WARPS;
 constexpr int kPx = 8;                 // pixels per lane (1x8 strip) = 4 packed pairs
 constexpr int kPairs = kPx / 2;
 constexpr int kBatch = 32;             // list entries staged per round (one per lane)
@@ -288,7 +292,7 @@ __device__ __forceinline__ int fwd_batch(const float4* srec, int cnt, int first_
 }
 
 template <bool kTrack>
-__global__ void __launch_bounds__(32, GS_FWD_MINB)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (GS_FWD_MINB + kWarpsPerCta - 1) / kWarpsPerCta)
 raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, int any_visible_host, const int64_t* __restrict__ counters_dev,
@@ -296,12 +300,16 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                   int32_t* __restrict__ flag_count, int rerun, float* __restrict__ image, float* __restrict__ alpha,
                   float* __restrict__ depth, float4* __restrict__ pix_state, int32_t* __restrict__ n_consumed,
                   int32_t* __restrict__ tile_consumed) {
-    __shared__ float4 srec[GS_PREFETCH ? 2 : 1][kBatch * 3];
+    __shared__ float4 srec_all[kWarpsPerCta][GS_PREFETCH ? 2 : 1][kBatch * 3];
+    float4 (*srec)[kBatch * 3] = srec_all[threadIdx.x >> 5];
 
-    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;      // any permutation of the tiles
+    // one warp per tile; warps never synchronise with each other, so a warp without a tile simply leaves
+    const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
+    if (slot >= tiles_x * ((img_h + kTile - 1) / kTile)) return;
+    const int tile = tile_order ? tile_order[slot] : slot;      // any permutation of the tiles
     // truncated lists: the re-run pass touches only the tiles the first pass flagged (usually none)
     if (rerun && (*flag_count == 0 || tile_flags[tile] == 0)) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int py = ty * kTile + (lane >> 1);
     const int px0 = tx * kTile + (lane & 1) * kPx;
@@ -368,13 +376,18 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     }
 #endif
 
-    if (range.y < full_end) {                       // stopped at the end of the stored prefix: did the tile need more?
+    if (list_cap > 0 && !rerun) {
+        // every tile writes its flag (the array needs no zero-fill): did the walk stop at the end of a stored prefix with
+        // pixels still alive?
         bool alive = false;
+        if (range.y < full_end) {
 #pragma unroll
-        for (int p = 0; p < kPairs; ++p) alive |= (A[p].x < kTermA) | (A[p].y < kTermA);
-        if (__any_sync(0xffffffffu, alive) && lane == 0) {
-            tile_flags[tile] = 1;
-            atomicAdd(flag_count, 1);
+            for (int p = 0; p < kPairs; ++p) alive |= (A[p].x < kTermA) | (A[p].y < kTermA);
+        }
+        const bool more = __any_sync(0xffffffffu, alive);
+        if (lane == 0) {
+            tile_flags[tile] = more ? 1 : 0;
+            if (more) atomicAdd(flag_count, 1);
         }
     }
 
@@ -604,7 +617,7 @@ __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane,
     }
 }
 
-__global__ void __launch_bounds__(32, GS_BWD_MINB)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (GS_BWD_MINB + kWarpsPerCta - 1) / kWarpsPerCta)
 raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, const float* __restrict__ alpha,
@@ -613,12 +626,17 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
                   const float* __restrict__ g_depth,
                   float* __restrict__ g_means2d, float* __restrict__ g_conics, float* __restrict__ g_depths,
                   float* __restrict__ g_colors, float* __restrict__ g_opac) {
-    __shared__ float4 srec[GS_PREFETCH ? 2 : 1][kBatch * 3];
-    __shared__ int sid[GS_PREFETCH ? 2 : 1][kBatch];
-    __shared__ __align__(16) float red[kBwdGroup * kRedVals * kRedStride + 16];
+    __shared__ float4 srec_all[kWarpsPerCta][GS_PREFETCH ? 2 : 1][kBatch * 3];
+    __shared__ int sid_all[kWarpsPerCta][GS_PREFETCH ? 2 : 1][kBatch];
+    __shared__ __align__(16) float red_all[kWarpsPerCta][kBwdGroup * kRedVals * kRedStride + 16];
+    float4 (*srec)[kBatch * 3] = srec_all[threadIdx.x >> 5];
+    int (*sid)[kBatch] = sid_all[threadIdx.x >> 5];
+    float* red = red_all[threadIdx.x >> 5];
 
-    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;      // any permutation of the tiles
-    const int lane = threadIdx.x;
+    const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
+    if (slot >= tiles_x * ((img_h + kTile - 1) / kTile)) return;
+    const int tile = tile_order ? tile_order[slot] : slot;      // any permutation of the tiles
+    const int lane = threadIdx.x & 31;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int py = ty * kTile + (lane >> 1);
     const int px0 = tx * kTile + (lane & 1) * kPx;
@@ -836,12 +854,12 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_consumed) {
-        raster_fwd_kernel<true><<<tiles_x * tiles_y, 32, 0, st>>>(
+        raster_fwd_kernel<true><<<(tiles_x * tiles_y + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
             counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
             n_consumed, tile_consumed);
     } else {
-        raster_fwd_kernel<false><<<tiles_x * tiles_y, 32, 0, st>>>(
+        raster_fwd_kernel<false><<<(tiles_x * tiles_y + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
             img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
             counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
             nullptr, tile_consumed);
@@ -854,6 +872,7 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
 extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, const int32_t* entry_ids,
                              const int32_t* tile_ranges, const float* splat_rec, const float* bg, const float* alpha,
                              const float* pix_state, const int32_t* tile_consumed, int32_t* tile_order_scratch,
+                             int32_t tile_order_ready,
                              const float* g_image, const float* g_alpha, const float* g_depth, float* g_means2d,
                              float* g_conics, float* g_depths, float* g_colors, float* g_opacities, void* stream) {
     const int rc = check_raster_args(img_w, img_h, tile_size, "gs_raster_bwd");
@@ -862,12 +881,12 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
                    g_conics && g_depths && g_colors && g_opacities, "NULL array argument");
     DeviceGuard guard(alpha);
     const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
-    if (tile_order_scratch) {
+    if (tile_order_scratch && !tile_order_ready) {
         tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tiles_x * tiles_y, tile_consumed, nullptr, tile_order_scratch);
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
     }
-    raster_bwd_kernel<<<tiles_x * tiles_y, 32, 0, (cudaStream_t)stream>>>(
+    raster_bwd_kernel<<<(tiles_x * tiles_y + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
         img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
         (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, g_depth, g_means2d, g_conics,
         g_depths, g_colors, g_opacities);

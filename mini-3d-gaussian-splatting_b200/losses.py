@@ -1,0 +1,116 @@
+"""Loss heads of the train step, fused into one pass over the rendered planes (csrc/loss.cu).
+
+The reference's step is ``l1_loss(rendered, gt)`` = ``|a - b|.mean()`` through torch ops and autograd
+(src/utils/loss.py, src/core/optimizer.py:137-139).  ``l1_loss`` below is that function as ONE kernel
+that also writes the gradient plane, so the backward pass of the loss launches nothing;
+``weighted_sum_loss`` is the linear loss of the parity tests and the benchmark, whose
+gradient is the weights themselves.
+
+Both return a ``FusedLoss``: it quacks like the scalar tensor a loss function returns
+(``backward()``, ``detach()``, ``item()``), so ``multiview_step`` / ``GaussianTrainer`` take it unchanged.
+CUDA only, like everything else here.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+_workspaces: Dict[int, torch.Tensor] = {}
+
+
+def _workspace(device: torch.device) -> torch.Tensor:
+    """One zero-initialised reduction workspace per device; the kernels leave it zeroed.  Calls on one device are
+    expected on one stream at a time (they are: the step's stream)."""
+    ws = _workspaces.get(device.index)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().gs_loss_workspace_bytes()), dtype=torch.uint8, device=device)
+        _workspaces[device.index] = ws
+    return ws
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class FusedLoss:
+    """A loss value that already knows d(loss)/d(input) for each of its inputs."""
+
+    def __init__(self, value: torch.Tensor, inputs: Sequence[torch.Tensor], grads: Sequence[torch.Tensor]):
+        self.value = value                      # 0-dim float32 tensor on the device
+        self._inputs = [t for t in inputs]
+        self._grads = [g for g in grads]
+
+    def backward(self) -> None:
+        pairs = [(t, g) for t, g in zip(self._inputs, self._grads) if t.requires_grad]
+        if pairs:
+            torch.autograd.backward([t for t, _ in pairs], [g for _, g in pairs])
+        self._inputs, self._grads = [], []
+
+    def detach(self) -> torch.Tensor:
+        return self.value.detach()
+
+    def item(self) -> float:
+        return float(self.value.item())
+
+    def __float__(self) -> float:
+        return self.item()
+
+
+def _check_cuda_f32(*tensors):
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError("fused losses run on CUDA tensors only; there is no CPU fallback")
+        if t.dtype != torch.float32:
+            raise TypeError(f"expected float32, got {t.dtype}")
+
+
+def weighted_sum_loss(inputs: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+                      coeffs: Optional[Sequence[float]] = None,
+                      grads: Optional[Sequence[torch.Tensor]] = None) -> FusedLoss:
+    """sum_k coeffs[k] * <inputs[k], weights[k]> in one launch (at most 4 terms).
+
+    `grads[k]` = coeffs[k] * weights[k] may be passed when the caller keeps the scaled weights around (the
+    benchmark does: they are the step's uploaded inputs); otherwise terms with coeff != 1 cost one scaling kernel."""
+    k = len(inputs)
+    if not 1 <= k <= 4 or len(weights) != k:
+        raise ValueError("1..4 (input, weight) pairs")
+    coeffs = [1.0] * k if coeffs is None else [float(c) for c in coeffs]
+    xs = [t.detach().contiguous() for t in inputs]
+    ws_ = [w.contiguous() for w in weights]
+    _check_cuda_f32(*xs, *ws_)
+    for x, w in zip(xs, ws_):
+        if x.numel() != w.numel():
+            raise ValueError(f"input {tuple(x.shape)} and weight {tuple(w.shape)} differ in size")
+    dev = xs[0].device
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    work = _workspace(dev)
+    P = ctypes.c_void_p * k
+    check(_lib.load().gs_weighted_sum(
+        k, P(*[t.data_ptr() for t in xs]), P(*[t.data_ptr() for t in ws_]),
+        (ctypes.c_int64 * k)(*[t.numel() for t in xs]), (ctypes.c_float * k)(*coeffs),
+        ptr(out), ptr(work), work.numel(), _stream(dev)), "gs_weighted_sum")
+    if grads is None:
+        grads = [w if c == 1.0 else w * c for w, c in zip(ws_, coeffs)]
+    return FusedLoss(out, list(inputs), [g.view_as(t) for g, t in zip(grads, inputs)])
+
+
+def l1_loss(rendered: torch.Tensor, target: torch.Tensor, scale: float = 1.0) -> FusedLoss:
+    """scale * mean|rendered - target| (src/utils/loss.py l1_loss) and its gradient, one kernel."""
+    x = rendered.detach().contiguous()
+    t = target.contiguous()
+    _check_cuda_f32(x, t)
+    if x.numel() != t.numel():
+        raise ValueError(f"rendered {tuple(x.shape)} and target {tuple(t.shape)} differ in size")
+    dev = x.device
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(x) if rendered.requires_grad else None
+    work = _workspace(dev)
+    check(_lib.load().gs_l1_loss(ptr(x), ptr(t), x.numel(), float(scale), ptr(grad), ptr(out), ptr(work), work.numel(),
+                                 _stream(dev)), "gs_l1_loss")
+    value = out if scale == 1.0 else out * scale
+    return FusedLoss(value, [rendered] if grad is not None else [], [grad.view_as(rendered)] if grad is not None else [])

@@ -12,6 +12,7 @@ CUDA only.  There is deliberately no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import math
 from dataclasses import dataclass
@@ -257,10 +258,16 @@ class _RasterizeFn(torch.autograd.Function):
         tile_ranges = torch.empty((tiles, 2), dtype=_I32, device=dev)
         # launch order of the tiles: heaviest first, by the work they had in the previous frame of this size
         # (any permutation gives the same image; a good one keeps full-size tiles out of the last wave)
-        bins.tile_order = torch.empty(tiles, dtype=_I32, device=dev)
-        prev = bins.prev_consumed if bins.fwd_order == "previous" else None
+        cached_order = bins.cached_order          # this camera's order by exact work from its previous visit ("camera" mode)
+        if cached_order is not None and (cached_order.numel() != tiles or cached_order.device != dev):
+            cached_order = None
+        prev = bins.prev_consumed if (bins.fwd_order == "previous" and cached_order is None) else None
         if prev is not None and (prev.numel() != tiles or prev.device != dev):
             prev = None
+        if cached_order is not None:
+            bins.tile_order = cached_order
+        else:
+            bins.tile_order = torch.empty(tiles, dtype=_I32, device=dev)
         if prev is not None:
             check(lib.gs_tile_order(tiles, ptr(prev), None, ptr(bins.tile_order), stream), "gs_tile_order")
 
@@ -269,25 +276,44 @@ class _RasterizeFn(torch.autograd.Function):
         # self-skipping completion launches, so the result never depends on `cap`
         cap = int(bins.list_cap or 0) if (bins.algo in (0, 1) and not track) else 0
         flag_bytes = (tiles + 3) // 4 * 4
-        flagbuf = torch.zeros(flag_bytes + 4, dtype=_U8, device=dev) if cap else None
+        # no zero-fill: gs_bin_sort zeroes the count, the first compositing pass writes every tile's flag
+        flagbuf = torch.empty(flag_bytes + 4, dtype=_U8, device=dev) if cap else None
         tile_flags = flagbuf[:tiles] if cap else None
         flag_count = flagbuf[flag_bytes:].view(_I32) if cap else None
+
+        # What the backward pass needs besides the forward's outputs -- the zeroed gradient slab its atomics add into and
+        # the tiles' launch order by exact work -- is produced on a side stream while this stream composites / evaluates
+        # the loss: the 44 MB fill has no dependency at all, the order needs only tile_consumed.
+        need_bwd = any(ctx.needs_input_grad) and n > 0
+        want_order = need_bwd or bins.fwd_order == "camera"       # the same order serves this camera's next forward
+        side = bins.side_stream() if want_order else None
+        slab = bwd_order = None
+        if side is not None:
+            main = torch.cuda.current_stream(dev)
+            ev = bins.side_events()
+            bwd_order = torch.empty(tiles, dtype=_I32, device=dev)
+            bwd_order.record_stream(side)
+            if need_bwd:
+                slab = torch.empty(n * 11, dtype=_F32, device=dev)
+                ev[0].record(main)               # the slab's memory may still be in use by kernels enqueued so far
+                side.wait_event(ev[0])
+                with torch.cuda.stream(side):
+                    slab.zero_()
+                slab.record_stream(side)
 
         def enqueue(num_sorted, d_size, counters_dev):
             entry_ids = torch.empty(max(d_size, 1), dtype=_I32, device=dev)
             ws_bytes = int(lib.gs_bin_workspace_bytes(num_sorted, d_size, tiles))
             ws = torch.empty(ws_bytes, dtype=_U8, device=dev)
-            if cap:
-                flagbuf.zero_()
             # this frame's list lengths give the forward's tile order: the flat counting sort emits it from the launch
             # that scans the tiles; the other algorithms need the separate kernel
-            fused_order = prev is None and int(bins.algo) == 1
+            fused_order = prev is None and cached_order is None and int(bins.algo) == 1
             with _timed("bin_sort", dev):
                 check(lib.gs_bin_sort(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
                                       ptr(bins.depth_keys), tiles_x, tiles, int(bins.algo), ptr(ws), ws.numel(),
                                       ptr(entry_ids), ptr(tile_ranges), None, counters_dev, cap,
-                                      ptr(bins.tile_order) if fused_order else None, stream), "gs_bin_sort")
-            if prev is None and not fused_order:
+                                      ptr(bins.tile_order) if fused_order else None, ptr(flag_count), stream), "gs_bin_sort")
+            if prev is None and cached_order is None and not fused_order:
                 check(lib.gs_tile_order(tiles, None, ptr(tile_ranges), ptr(bins.tile_order), stream), "gs_tile_order")
             vis_host = int(bins.num_vis > 0) if counters_dev is None else 0
 
@@ -321,6 +347,16 @@ class _RasterizeFn(torch.autograd.Function):
         bins.entry_ids, bins.tile_ranges = entry_ids, tile_ranges
         bins.renderer_consumed[(dev.index, W, H)] = tile_consumed
 
+        ctx.side = None
+        if side is not None:
+            ev[1].record(main)                   # tile_consumed is final
+            side.wait_event(ev[1])
+            check(lib.gs_tile_order(tiles, ptr(tile_consumed), None, ptr(bwd_order),
+                                    ctypes.c_void_p(side.cuda_stream)), "gs_tile_order")
+            ev[2].record(side)
+            bins.new_order = (bwd_order, ev[2])
+            if need_bwd:
+                ctx.side = (ev[2], slab, bwd_order)
         ctx.meta = meta
         ctx.set_materialize_grads(False)
         ctx.any_visible = bins.num_vis > 0
@@ -339,8 +375,15 @@ class _RasterizeFn(torch.autograd.Function):
         n = ctx.n
         dev = rec.device
         H, W = meta.H, meta.W
-        # one zeroed slab carved into the five contiguous gradient tensors (atomics accumulate into it)
-        slab = torch.zeros(n * 11, dtype=_F32, device=dev)
+        # one zeroed slab carved into the five contiguous gradient tensors (atomics accumulate into it); zero-filled, like
+        # the tile order below, on the side stream during the forward pass
+        order = None
+        if ctx.side is not None:
+            side_done, slab, order = ctx.side
+            ctx.side = None                      # a second backward through the same graph gets a fresh slab
+            torch.cuda.current_stream(dev).wait_event(side_done)
+        else:
+            slab = torch.zeros(n * 11, dtype=_F32, device=dev)
         # float4-read array first, then the float2 one: both stay naturally aligned for any n
         g_conics = slab[0:4 * n].view(n, 2, 2)
         g_means2d = slab[4 * n:6 * n].view(n, 2)
@@ -354,10 +397,12 @@ class _RasterizeFn(torch.autograd.Function):
                 return g.contiguous()
 
             gi, ga, gd = dense(g_image, 3), dense(g_alpha, 1), dense(g_depth, 1)
-            order = torch.empty(tile_consumed.numel(), dtype=_I32, device=dev)      # heaviest tiles first (exact work)
+            scratch = None
+            if order is None:                    # heaviest tiles first (exact work): ordered inside gs_raster_bwd
+                order = scratch = torch.empty(tile_consumed.numel(), dtype=_I32, device=dev)
             with _timed("raster_bwd", dev):
                 check(lib.gs_raster_bwd(W, H, meta.tile, ptr(entry_ids), ptr(tile_ranges), ptr(rec), ptr(bg), ptr(alpha),
-                                        ptr(pix_state), ptr(tile_consumed), ptr(order), ptr(gi), ptr(ga), ptr(gd),
+                                        ptr(pix_state), ptr(tile_consumed), ptr(order), int(scratch is None), ptr(gi), ptr(ga), ptr(gd),
                                         ptr(g_means2d), ptr(g_conics), ptr(g_depths), ptr(g_colors), ptr(g_opac),
                                         _stream(dev)), "gs_raster_bwd")
         return None, None, g_means2d, g_conics, g_depths, g_colors, g_opac, None, None, None
@@ -377,6 +422,8 @@ class _FrameBins:
         self._host, self._event = slot
         self.renderer_consumed = renderer._tile_consumed
         self.prev_consumed = None
+        self.cached_order = None
+        self.new_order = None
         self.tile_order = None
         self.fwd_order = renderer.fwd_tile_order
         self._renderer = renderer
@@ -398,6 +445,20 @@ class _FrameBins:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self._renderer._cap_feedback[self.device.index] = (slot, ev)
+
+    def side_stream(self):
+        """Per-device side stream for work the backward pass will need (None when disabled)."""
+        r = self._renderer
+        if not r.side_stream_prep:
+            return None
+        s_ = r._side.get(self.device.index)
+        if s_ is None:
+            s_ = r._side[self.device.index] = (torch.cuda.Stream(device=self.device),
+                                               [torch.cuda.Event() for _ in range(3)])
+        return s_[0]
+
+    def side_events(self):
+        return self._renderer._side[self.device.index][1]
 
     def start_readback(self):
         self._host.copy_(self.counters, non_blocking=True)
@@ -457,12 +518,22 @@ class GaussianRenderer:
         self._d_cap: Dict[int, Optional[int]] = {}
         self._readback: Dict[int, tuple] = {}
         self._tile_consumed: Dict[tuple, torch.Tensor] = {}     # last frame's per-tile work per (device, W, H)
-        # work estimate behind the forward's tile launch order: "ranges" = this frame's list lengths,
-        # "previous" = what the tiles consumed in the previous frame of the same size (falls back to "ranges")
-        self.fwd_tile_order = "ranges"
+        # work estimate behind the forward's tile launch order:
+        #   "camera"   (default) the order by exact work (tile_consumed) from the last time THIS camera was rendered -- a
+        #              training loop visits its cameras once per epoch, the scene moves little in between; the order is the
+        #              one that frame's backward pass used, kept per camera (LRU of `camera_cache_size` poses, 32 KB each
+        #              at 1080p), so a hit costs no kernel at all; a camera seen for the first time falls back to "ranges";
+        #   "ranges"   this frame's list lengths (stateless; emitted by the binning's tile scan);
+        #   "previous" what the tiles consumed in the previous frame of the same size, whatever its camera.
+        self.fwd_tile_order = "camera"
+        self.camera_cache_size = 1024
+        self._order_by_camera = collections.OrderedDict()
         # truncated tile lists: entries stored / composited per tile before the completion path kicks in (0 = complete
         # lists).  Doubled automatically when a frame had to complete tiles.
         self.list_cap = 1024
+        # slab zero-fill and backward tile order on a side stream during the forward pass (see _RasterizeFn.forward)
+        self.side_stream_prep = True
+        self._side: Dict[int, tuple] = {}
         self._cap_feedback: Dict[int, Optional[tuple]] = {}
         self._cap_pinned: Dict[int, torch.Tensor] = {}
         _lib.load()   # fail at construction, not at first render, if the extension is missing
@@ -575,6 +646,13 @@ class GaussianRenderer:
         stream = _stream(device)
         bins = _FrameBins(self, device)
         bins.prev_consumed = self._tile_consumed.get((device.index, W, H))
+        cam_key = (device.index, W, H, T, bytes(meta.cam))
+        if self.fwd_tile_order == "camera" and self.side_stream_prep:
+            hit = self._order_by_camera.get(cam_key)
+            if hit is not None:
+                self._order_by_camera.move_to_end(cam_key)
+                torch.cuda.current_stream(device).wait_event(hit[1])      # written on the side stream, long since
+                bins.cached_order = hit[0]
         # 0 = the flat counting sort.  3 (blocked two-level sort, coalesced final stores) is bit-identical and
         # measured no faster (385 vs 376 us at config[1]); it needs rectangles of at most 8 tiles per side
         algo = self.bin_algo if self.bin_algo else (1 if num_tiles <= MAX_COUNTING_TILES else 2)
@@ -600,6 +678,10 @@ class GaussianRenderer:
         entry_ids, tile_ranges, sorted_ids = bins.entry_ids, bins.tile_ranges, bins.sorted_ids
         # capacity for the next frame's optimistic binning: this frame's pair count plus a quarter
         # (gs_bin_sort addresses pairs with int32: a capacity beyond that falls back to exact sizes)
+        if bins.new_order is not None and self.fwd_tile_order == "camera":
+            self._order_by_camera[cam_key] = bins.new_order
+            while len(self._order_by_camera) > self.camera_cache_size:
+                self._order_by_camera.popitem(last=False)
         cap_next = int(D * 1.25) + 4096
         self._d_cap[device.index] = cap_next if (self.optimistic_binning and cap_next < (1 << 31)) else None
 

@@ -191,8 +191,14 @@ class DensityController:
         return {"split": split, "cloned": cloned, "pruned": pruned, "points": model.get_num_points(), "src_row": src_row}
 
 
-def l1_loss(image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    """The L1 term of the reference's loss (loss.py:52); its SSIM term does not run (loss.py:26,39)."""
+def l1_loss(image: torch.Tensor, target: torch.Tensor):
+    """The L1 term of the reference's loss (loss.py:52); its SSIM term does not run (loss.py:26,39).
+    On the device: one fused kernel that also writes the gradient plane (losses.l1_loss, csrc/loss.cu), so the
+    loss's backward launches nothing.  Host tensors (the CPU tests of the step logic with a stand-in renderer) go
+    through the two torch ops of the reference."""
+    if image.is_cuda:
+        from .losses import l1_loss as fused_l1
+        return fused_l1(image, target)
     return (image - target).abs().mean()
 
 

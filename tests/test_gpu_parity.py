@@ -274,7 +274,7 @@ def test_sort_keys_bit_exact_vs_oracle():
     for algo in (1, 2, 3):       # flat counting sort, library radix sort, blocked counting sort: identical sequences
         entry_ids.fill_(-1); ekeys.fill_(-1)
         _lib.check(lib.gs_bin_sort(n, ns, D, P(sorted_ids), P(offsets), P(dbg["tile_rect"]), P(dbg["depth_keys"]), 20, num_tiles,
-                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, 0, P(order) if algo == 1 else None, st), "sort")
+                                   algo, P(ws), wsb, P(entry_ids), P(ranges), P(ekeys), None, 0, P(order) if algo == 1 else None, None, st), "sort")
         assert torch.equal(ekeys.cpu(), o["sort_keys"]), algo
         assert torch.equal(entry_ids.cpu().long(), o["sort_ids"]), algo
         util.assert_same_ranges(ranges, o["tile_ranges"])

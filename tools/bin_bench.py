@@ -40,7 +40,7 @@ for algo in (1, 2, 3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         check(lib.gs_bin_sort(N, num_sorted, D, ptr(sorted_ids), ptr(offsets), ptr(dbg["tile_rect"]), ptr(dbg["depth_keys"]),
-                              tiles_x, tiles, algo, ptr(ws), ws.numel(), ptr(entry), ptr(ranges), None, None, 0, None, ctypes.c_void_p(stream)), "bin")
+                              tiles_x, tiles, algo, ptr(ws), ws.numel(), ptr(entry), ptr(ranges), None, None, 0, None, None, ctypes.c_void_p(stream)), "bin")
         b.record(); torch.cuda.synchronize()
         if r >= 2: ts.append(a.elapsed_time(b))
     if ref is None: ref = (entry.clone(), ranges.clone())
