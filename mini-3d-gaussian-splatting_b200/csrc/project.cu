@@ -250,7 +250,7 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
                    const float* __restrict__ rotation, const float* __restrict__ cov3d,
                    const float* __restrict__ opacity, int opacity_is_logit,
                    const float* __restrict__ feat0, int64_t feat_stride, ShParams sh, Camera cam,
-                   int img_w, int img_h, int tiles_x_unused, float rmin, float rmax,
+                   int img_w, int img_h, int tile_size, float rmin, float rmax,
                    float2* __restrict__ means2d, float* __restrict__ depths, float4* __restrict__ conics,
                    float* __restrict__ radii, float* __restrict__ colors, float* __restrict__ opac_out,
                    uint8_t* __restrict__ vis_out, int32_t* __restrict__ tiles_touched,
@@ -309,8 +309,8 @@ project_fwd_kernel(int64_t n, const float* __restrict__ xyz, const float* __rest
         const int px0 = max(ix - ir, 0), px1 = min(ix + 1 + ir, img_w);
         const int py0 = max(iy - ir, 0), py1 = min(iy + 1 + ir, img_h);
         if (px0 < px1 && py0 < py1) {
-            const int tx0 = px0 / kTile, tx1 = (px1 - 1) / kTile;
-            const int ty0 = py0 / kTile, ty1 = (py1 - 1) / kTile;
+            const int tx0 = px0 / tile_size, tx1 = (px1 - 1) / tile_size;      // any tile size (renderer.py:24, :286-289)
+            const int ty0 = py0 / tile_size, ty1 = (py1 - 1) / tile_size;
             cnt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
             rect = make_ushort4((unsigned short)tx0, (unsigned short)ty0, (unsigned short)tx1, (unsigned short)ty1);
         }
@@ -610,11 +610,9 @@ extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_
     GS_REQUIRE(n >= 0, "n < 0");
     GS_REQUIRE(camera_host != nullptr, "camera_host is NULL");
     GS_REQUIRE(img_w > 0 && img_h > 0, "image size must be positive");
-    if (tile_size != kTile) {
-        set_error("gs_project_fwd: tile_size %d unsupported (kernels are built for %d)", tile_size, kTile);
-        return GS_ERR_UNSUPPORTED;
-    }
-    GS_REQUIRE((img_w + kTile - 1) / kTile <= 65535 && (img_h + kTile - 1) / kTile <= 65535, "image too large for uint16 tile rects");
+    GS_REQUIRE(tile_size >= 1 && tile_size <= 4096, "tile_size out of range");
+    GS_REQUIRE((img_w + tile_size - 1) / tile_size <= 65535 && (img_h + tile_size - 1) / tile_size <= 65535,
+               "image too large for uint16 tile rects");
     if (n == 0) return GS_OK;
     const bool param_mode = scaling_log != nullptr && rotation != nullptr;
     GS_REQUIRE(param_mode || cov3d != nullptr, "need (scaling_log, rotation) or cov3d");
@@ -632,7 +630,7 @@ extern "C" int gs_project_fwd(int64_t n, const float* xyz, const float* scaling_
     if (param_mode) {
 #define GS_LAUNCH_FWD(PM, SH)                                                                                          \
     project_fwd_kernel<PM, SH><<<blocks, threads, smem, st>>>(                                                       \
-        n, xyz, scaling_log, rotation, cov3d, opacity, opacity_is_logit, feat0, feat_stride, sh, cam, img_w, img_h, 0, \
+        n, xyz, scaling_log, rotation, cov3d, opacity, opacity_is_logit, feat0, feat_stride, sh, cam, img_w, img_h, tile_size, \
         radius_min, radius_max, (float2*)means2d, depths, (float4*)conics, radii, colors, opacities, vis,             \
         tiles_touched, (ushort4*)tile_rect, depth_keys, (float4*)splat_rec)
         if (sh.degree > 0) GS_LAUNCH_FWD(true, true); else GS_LAUNCH_FWD(true, false);

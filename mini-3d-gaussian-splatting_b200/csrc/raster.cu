@@ -291,9 +291,43 @@ __device__ __forceinline__ int fwd_batch(const float4* srec, int cnt, int first_
     return done;
 }
 
+// Tile geometry for any tile size (the reference takes any, renderer.py:24).  A warp always works on a 16x16 pixel block
+// (32 lanes x 1x8 strips).  A tile of T x T pixels is covered by sub x sub such blocks, sub = ceil(T / 16), each walked
+// by its own warp over the tile's list; pixels of a block beyond the tile's (or the image's) edge are masked for good
+// (the "never alive" sentinel).  T = 16: one block per tile and nothing to mask inside the image; T < 16: one block per
+// tile with the lanes outside the T x T corner idle; T > 16: the blocks of a tile stop independently.
+// A launch SLOT is one (tile, block) pair: slot = tile * sub^2 + block; tile_order / tile_consumed are indexed by slot.
+struct TileGeom {
+    int tile_size, tiles_x, tiles_y, sub;
+};
+__host__ __device__ inline TileGeom tile_geom(int img_w, int img_h, int tile_size) {
+    TileGeom g;
+    g.tile_size = tile_size;
+    g.tiles_x = (img_w + tile_size - 1) / tile_size;
+    g.tiles_y = (img_h + tile_size - 1) / tile_size;
+    g.sub = (tile_size + kTile - 1) / kTile;
+    return g;
+}
+struct WarpBlock {
+    int tile, px0, py, x_lim, y_lim;
+};
+__device__ __forceinline__ WarpBlock locate_block(const TileGeom& g, int slot_id, int lane, int img_w, int img_h) {
+    WarpBlock b;
+    const int per_tile = g.sub * g.sub;
+    b.tile = slot_id / per_tile;
+    const int blk = slot_id - b.tile * per_tile;
+    const int by = blk / g.sub, bx = blk - by * g.sub;
+    const int ty = b.tile / g.tiles_x, tx = b.tile - ty * g.tiles_x;
+    b.x_lim = min(img_w, (tx + 1) * g.tile_size);
+    b.y_lim = min(img_h, (ty + 1) * g.tile_size);
+    b.py = ty * g.tile_size + by * kTile + (lane >> 1);
+    b.px0 = tx * g.tile_size + bx * kTile + (lane & 1) * kPx;
+    return b;
+}
+
 template <bool kTrack>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, (GS_FWD_MINB + kWarpsPerCta - 1) / kWarpsPerCta)
-raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
+raster_fwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, int any_visible_host, const int64_t* __restrict__ counters_dev,
                   const int32_t* __restrict__ tile_order, int list_cap, uint8_t* __restrict__ tile_flags,
@@ -305,14 +339,14 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 
     // one warp per tile; warps never synchronise with each other, so a warp without a tile simply leaves
     const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
-    if (slot >= tiles_x * ((img_h + kTile - 1) / kTile)) return;
-    const int tile = tile_order ? tile_order[slot] : slot;      // any permutation of the tiles
-    // truncated lists: the re-run pass touches only the tiles the first pass flagged (usually none)
-    if (rerun && (*flag_count == 0 || tile_flags[tile] == 0)) return;
+    if (slot >= geom.tiles_x * geom.tiles_y * geom.sub * geom.sub) return;
+    const int slot_id = tile_order ? tile_order[slot] : slot;      // any permutation of the slots
     const int lane = threadIdx.x & 31;
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int py = ty * kTile + (lane >> 1);
-    const int px0 = tx * kTile + (lane & 1) * kPx;
+    const WarpBlock wb = locate_block(geom, slot_id, lane, img_w, img_h);
+    const int tile = wb.tile;
+    // truncated lists (tile sizes <= 16 only: slot == tile): the re-run pass touches only the tiles the first pass flagged
+    if (rerun && (*flag_count == 0 || tile_flags[tile] == 0)) return;
+    const int py = wb.py, px0 = wb.px0;
     const float bg0 = bg_ptr[0], bg1 = bg_ptr[1], bg2 = bg_ptr[2];
     const float fpy = (float)py;
     const bool any_visible = counters_dev ? (counters_dev[2] > 0) : (any_visible_host != 0);
@@ -321,8 +355,8 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     int ncons[kPx];
 #pragma unroll
     for (int p = 0; p < kPairs; ++p) {
-        const bool in0 = (px0 + 2 * p < img_w) && (py < img_h);
-        const bool in1 = (px0 + 2 * p + 1 < img_w) && (py < img_h);
+        const bool in0 = (px0 + 2 * p < wb.x_lim) && (py < wb.y_lim);
+        const bool in1 = (px0 + 2 * p + 1 < wb.x_lim) && (py < wb.y_lim);
         fpx[p] = make_float2((float)(px0 + 2 * p), (float)(px0 + 2 * p + 1));
         A[p] = make_float2(in0 ? 0.f : 2.0f, in1 ? 0.f : 2.0f);          // 2.0: never alive
         Ds[p] = bc2(0.f);
@@ -396,9 +430,9 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
         const int px = px0 + k;
-        if (px < img_w && py < img_h) {
+        const float Ak = (k & 1) ? A[k >> 1].y : A[k >> 1].x;
+        if (Ak < 1.5f) {                            // pixels outside the tile / image kept the 2.0 sentinel
             const int64_t p = (int64_t)py * img_w + px;
-            const float Ak = (k & 1) ? A[k >> 1].y : A[k >> 1].x;
             const float Crk = (k & 1) ? Cr[k >> 1].y : Cr[k >> 1].x;
             const float Cgk = (k & 1) ? Cg[k >> 1].y : Cg[k >> 1].x;
             const float Cbk = (k & 1) ? Cb[k >> 1].y : Cb[k >> 1].x;
@@ -424,7 +458,7 @@ raster_fwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
         }
     }
     // entries this tile loaded (batch granular): bounds the backward walk; the E of the byte formulas
-    if (lane == 0) tile_consumed[tile] = walked;
+    if (lane == 0) tile_consumed[slot_id] = walked;
 }
 
 // Backward: re-walks the list front to back with the forward's recurrence.  With
@@ -618,7 +652,7 @@ __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane,
 }
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta, (GS_BWD_MINB + kWarpsPerCta - 1) / kWarpsPerCta)
-raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__ entry_ids,
+raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
                   const float* __restrict__ bg_ptr, const float* __restrict__ alpha,
                   const float4* __restrict__ pix_state, const int32_t* __restrict__ tile_consumed,
@@ -634,12 +668,12 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     float* red = red_all[threadIdx.x >> 5];
 
     const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
-    if (slot >= tiles_x * ((img_h + kTile - 1) / kTile)) return;
-    const int tile = tile_order ? tile_order[slot] : slot;      // any permutation of the tiles
+    if (slot >= geom.tiles_x * geom.tiles_y * geom.sub * geom.sub) return;
+    const int slot_id = tile_order ? tile_order[slot] : slot;      // any permutation of the slots
     const int lane = threadIdx.x & 31;
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int py = ty * kTile + (lane >> 1);
-    const int px0 = tx * kTile + (lane & 1) * kPx;
+    const WarpBlock wb = locate_block(geom, slot_id, lane, img_w, img_h);
+    const int tile = wb.tile;
+    const int py = wb.py, px0 = wb.px0;
     const float bg0 = bg_ptr[0], bg1 = bg_ptr[1], bg2 = bg_ptr[2];
     const float fpy = (float)py;
     const int64_t plane = (int64_t)img_w * img_h;
@@ -672,7 +706,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int px = px0 + 2 * p + h;
-            const bool inside = px < img_w && py < img_h;
+            const bool inside = px < wb.x_lim && py < wb.y_lim;
             Ai[h] = inside ? 0.f : 2.0f;
             Ti[h] = gr[h] = gg[h] = gb[h] = gd_[h] = ga_[h] = 0.f;
             if (inside) {
@@ -709,7 +743,7 @@ raster_bwd_kernel(int img_w, int img_h, int tiles_x, const int32_t* __restrict__
     out.sid = sid[0];
 
     const int2 range = tile_ranges[tile];
-    const int end = range.x + tile_consumed[tile];
+    const int end = range.x + tile_consumed[slot_id];
 #if GS_PREFETCH
     int buf = 0;
     int id_cur = -1;
@@ -832,9 +866,9 @@ static int check_raster_args(int32_t img_w, int32_t img_h, int32_t tile_size, co
         set_error("%s: image size must be positive", fn);
         return GS_ERR_INVALID_ARGUMENT;
     }
-    if (tile_size != kTile) {
-        set_error("%s: tile_size %d unsupported (kernels are built for %d)", fn, tile_size, kTile);
-        return GS_ERR_UNSUPPORTED;
+    if (tile_size < 1 || tile_size > 4096) {
+        set_error("%s: tile_size %d out of range", fn, tile_size);
+        return GS_ERR_INVALID_ARGUMENT;
     }
     return GS_OK;
 }
@@ -850,17 +884,21 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     GS_REQUIRE(tile_ranges && bg && image && alpha && depth && pix_state && tile_consumed, "NULL array argument");
     GS_REQUIRE((list_cap <= 0 && !rerun) || (tile_flags && flag_count), "truncated lists need tile_flags and flag_count");
     if (list_cap <= 0) list_cap = 0;
+    GS_REQUIRE((list_cap == 0 && !rerun) || tile_size <= kTile, "truncated lists need tile_size <= 16 (one warp per tile)");
     DeviceGuard guard(image);
-    const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
+    const TileGeom geom = tile_geom(img_w, img_h, tile_size);
+    const int64_t slots64 = (int64_t)geom.tiles_x * geom.tiles_y * geom.sub * geom.sub;
+    GS_REQUIRE(slots64 < (1ll << 31), "too many tiles");
+    const int slots = (int)slots64;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_consumed) {
-        raster_fwd_kernel<true><<<(tiles_x * tiles_y + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
-            img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
+        raster_fwd_kernel<true><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
+            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
             counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
             n_consumed, tile_consumed);
     } else {
-        raster_fwd_kernel<false><<<(tiles_x * tiles_y + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
-            img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
+        raster_fwd_kernel<false><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
+            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
             counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
             nullptr, tile_consumed);
     }
@@ -880,14 +918,17 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     GS_REQUIRE(tile_ranges && bg && alpha && pix_state && tile_consumed && g_image && g_alpha && g_depth && g_means2d &&
                    g_conics && g_depths && g_colors && g_opacities, "NULL array argument");
     DeviceGuard guard(alpha);
-    const int tiles_x = (img_w + kTile - 1) / kTile, tiles_y = (img_h + kTile - 1) / kTile;
+    const TileGeom geom = tile_geom(img_w, img_h, tile_size);
+    const int64_t slots64 = (int64_t)geom.tiles_x * geom.tiles_y * geom.sub * geom.sub;
+    GS_REQUIRE(slots64 < (1ll << 31), "too many tiles");
+    const int slots = (int)slots64;
     if (tile_order_scratch && !tile_order_ready) {
-        tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tiles_x * tiles_y, tile_consumed, nullptr, tile_order_scratch);
+        tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(slots, tile_consumed, nullptr, tile_order_scratch);
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
     }
-    raster_bwd_kernel<<<(tiles_x * tiles_y + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
-        img_w, img_h, tiles_x, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
+    raster_bwd_kernel<<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
+        img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
         (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, g_depth, g_means2d, g_conics,
         g_depths, g_colors, g_opacities);
     GS_CUDA_TRY(cudaGetLastError());

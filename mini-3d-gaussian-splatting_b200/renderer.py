@@ -24,7 +24,7 @@ import torch
 from . import _lib
 from ._lib import check, ptr
 
-SUPPORTED_TILE_SIZES = (16,)
+RASTER_BLOCK = 16                 # csrc/raster.cu: a warp composites a 16x16 pixel block; a tile is ceil(T/16)^2 of them
 MAX_COUNTING_TILES = 200000       # csrc/binsort.cu kMaxCountingTiles: one byte of shared memory per tile
 _U8 = torch.uint8
 _I32 = torch.int32
@@ -247,6 +247,8 @@ class _RasterizeFn(torch.autograd.Function):
         n = means2d.shape[0]
         tiles_x, tiles_y = (W + T - 1) // T, (H + T - 1) // T
         tiles = tiles_x * tiles_y
+        sub = (T + RASTER_BLOCK - 1) // RASTER_BLOCK
+        slots = tiles * sub * sub             # launch slots of the compositing kernels: (tile, 16x16 block) pairs
         stream = _stream(dev)
         image = torch.empty((3, H, W), dtype=_F32, device=dev)
         alpha = torch.empty((1, H, W), dtype=_F32, device=dev)
@@ -254,27 +256,32 @@ class _RasterizeFn(torch.autograd.Function):
         pix_state = torch.empty((H * W, 4), dtype=_F32, device=dev)
         # per-pixel consumed-entry counts: debug / parity output only (RenderSettings.debug)
         n_consumed = torch.empty((H, W), dtype=_I32, device=dev) if track else None
-        tile_consumed = torch.empty((tiles,), dtype=_I32, device=dev)
+        tile_consumed = torch.empty((slots,), dtype=_I32, device=dev)
         tile_ranges = torch.empty((tiles, 2), dtype=_I32, device=dev)
         # launch order of the tiles: heaviest first, by the work they had in the previous frame of this size
         # (any permutation gives the same image; a good one keeps full-size tiles out of the last wave)
         cached_order = bins.cached_order          # this camera's order by exact work from its previous visit ("camera" mode)
-        if cached_order is not None and (cached_order.numel() != tiles or cached_order.device != dev):
+        if cached_order is not None and (cached_order.numel() != slots or cached_order.device != dev):
             cached_order = None
         prev = bins.prev_consumed if (bins.fwd_order == "previous" and cached_order is None) else None
-        if prev is not None and (prev.numel() != tiles or prev.device != dev):
+        if prev is not None and (prev.numel() != slots or prev.device != dev):
             prev = None
+        # tiles larger than a block: the list lengths are per tile, not per slot -- without an estimate per slot (this
+        # camera's previous visit, or the previous frame) the slots are taken in natural order
+        ranges_order = sub == 1
         if cached_order is not None:
             bins.tile_order = cached_order
+        elif prev is not None or ranges_order:
+            bins.tile_order = torch.empty(slots, dtype=_I32, device=dev)
         else:
-            bins.tile_order = torch.empty(tiles, dtype=_I32, device=dev)
+            bins.tile_order = None
         if prev is not None:
-            check(lib.gs_tile_order(tiles, ptr(prev), None, ptr(bins.tile_order), stream), "gs_tile_order")
+            check(lib.gs_tile_order(slots, ptr(prev), None, ptr(bins.tile_order), stream), "gs_tile_order")
 
         # truncated lists (flat counting sort, not in debug mode): store and composite only each tile's first
         # `cap` list entries; a tile that needs more is flagged, completed and composited again by the two
         # self-skipping completion launches, so the result never depends on `cap`
-        cap = int(bins.list_cap or 0) if (bins.algo in (0, 1) and not track) else 0
+        cap = int(bins.list_cap or 0) if (bins.algo in (0, 1) and not track and sub == 1) else 0
         flag_bytes = (tiles + 3) // 4 * 4
         # no zero-fill: gs_bin_sort zeroes the count, the first compositing pass writes every tile's flag
         flagbuf = torch.empty(flag_bytes + 4, dtype=_U8, device=dev) if cap else None
@@ -291,7 +298,7 @@ class _RasterizeFn(torch.autograd.Function):
         if side is not None:
             main = torch.cuda.current_stream(dev)
             ev = bins.side_events()
-            bwd_order = torch.empty(tiles, dtype=_I32, device=dev)
+            bwd_order = torch.empty(slots, dtype=_I32, device=dev)
             bwd_order.record_stream(side)
             if need_bwd:
                 slab = torch.empty(n * 11, dtype=_F32, device=dev)
@@ -307,13 +314,13 @@ class _RasterizeFn(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=_U8, device=dev)
             # this frame's list lengths give the forward's tile order: the flat counting sort emits it from the launch
             # that scans the tiles; the other algorithms need the separate kernel
-            fused_order = prev is None and cached_order is None and int(bins.algo) == 1
+            fused_order = prev is None and cached_order is None and ranges_order and int(bins.algo) == 1
             with _timed("bin_sort", dev):
                 check(lib.gs_bin_sort(n, num_sorted, d_size, ptr(bins.sorted_ids), ptr(bins.offsets), ptr(bins.tile_rect),
                                       ptr(bins.depth_keys), tiles_x, tiles, int(bins.algo), ptr(ws), ws.numel(),
                                       ptr(entry_ids), ptr(tile_ranges), None, counters_dev, cap,
                                       ptr(bins.tile_order) if fused_order else None, ptr(flag_count), stream), "gs_bin_sort")
-            if prev is None and cached_order is None and not fused_order:
+            if prev is None and cached_order is None and ranges_order and not fused_order:
                 check(lib.gs_tile_order(tiles, None, ptr(tile_ranges), ptr(bins.tile_order), stream), "gs_tile_order")
             vis_host = int(bins.num_vis > 0) if counters_dev is None else 0
 
@@ -345,13 +352,13 @@ class _RasterizeFn(torch.autograd.Function):
         if cap:
             bins.report_flagged(flag_count)         # asynchronous: the next frame doubles the cap if tiles were flagged
         bins.entry_ids, bins.tile_ranges = entry_ids, tile_ranges
-        bins.renderer_consumed[(dev.index, W, H)] = tile_consumed
+        bins.renderer_consumed[(dev.index, W, H, T)] = tile_consumed
 
         ctx.side = None
         if side is not None:
             ev[1].record(main)                   # tile_consumed is final
             side.wait_event(ev[1])
-            check(lib.gs_tile_order(tiles, ptr(tile_consumed), None, ptr(bwd_order),
+            check(lib.gs_tile_order(slots, ptr(tile_consumed), None, ptr(bwd_order),
                                     ctypes.c_void_p(side.cuda_stream)), "gs_tile_order")
             ev[2].record(side)
             bins.new_order = (bwd_order, ev[2])
@@ -499,9 +506,10 @@ class GaussianRenderer:
         if not 0 <= int(sh_degree) <= 3:
             raise ValueError("sh_degree must be 0..3")
         self.sh_degree = int(sh_degree)
-        if int(tile_size) not in SUPPORTED_TILE_SIZES:
-            # the reference takes any tile size (renderer.py:24); the kernels here are specialised per size
-            raise ValueError(f"tile_size must be one of {SUPPORTED_TILE_SIZES}, got {tile_size}")
+        # any tile size, as the reference (renderer.py:24): the kernels composite 16x16 pixel blocks, a tile is covered by
+        # ceil(T/16)^2 of them (16 is the fast case: one block per tile, nothing masked; truncated lists need T <= 16)
+        if not 1 <= int(tile_size) <= 4096:
+            raise ValueError(f"tile_size must be in 1..4096, got {tile_size}")
         self.tile_size = int(tile_size)
         self.radius_min = radius_min
         self.radius_max = radius_max
@@ -645,7 +653,7 @@ class GaussianRenderer:
         num_tiles = tiles_x * tiles_y
         stream = _stream(device)
         bins = _FrameBins(self, device)
-        bins.prev_consumed = self._tile_consumed.get((device.index, W, H))
+        bins.prev_consumed = self._tile_consumed.get((device.index, W, H, T))
         cam_key = (device.index, W, H, T, bytes(meta.cam))
         if self.fwd_tile_order == "camera" and self.side_stream_prep:
             hit = self._order_by_camera.get(cam_key)

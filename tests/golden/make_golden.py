@@ -97,6 +97,14 @@ CASES = {
                                 bg=(0.25, 0.1, 0.4), scale_boost=math.log(10.0), opacity_boost=1.0),
     "aniso_n200_96x64_bigsplats": dict(scene="aniso", n=200, seed=11, W=96, H=64, cam=("c0",),
                                        bg=(0.6, 0.6, 0.6), scale_boost=math.log(25.0), opacity_boost=-1.0),
+    # other tile sizes (renderer.py:24 takes any): which splats a pixel sees depends on its tile's list (3-sigma rectangles
+    # against tiles, renderer.py:263-298), so the image itself changes with the tile size
+    "aniso_n100_48x40_tile8": dict(scene="aniso", n=100, seed=13, W=48, H=40, cam=("orbit", 2, 9), tile=8,
+                                   bg=(0.1, 0.3, 0.2), scale_boost=math.log(6.0), opacity_boost=1.0),
+    "aniso_n90_50x44_tile12": dict(scene="aniso", n=90, seed=17, W=50, H=44, cam=("orbit", 5, 9), tile=12,
+                                   bg=(0.3, 0.1, 0.2), scale_boost=math.log(7.0), opacity_boost=1.5),
+    "aniso_n100_72x56_tile32": dict(scene="aniso", n=100, seed=19, W=72, H=56, cam=("c0",), tile=32,
+                                    bg=(0.2, 0.2, 0.5), scale_boost=math.log(6.0), opacity_boost=2.0),
 }
 
 
@@ -120,7 +128,7 @@ def run_reference(spec, s, cam):
     m._scaling, m._rotation, m._opacity = P(s["scaling"].clone()), P(s["rotation"].clone()), P(s["opacity"].clone())
     H, W = spec["H"], spec["W"]
     settings = RenderSettings(image_height=H, image_width=W, bg_color=torch.tensor(spec["bg"], dtype=torch.float32))
-    rd = GaussianRenderer(tile_size=16, radius_min=0.01, radius_max=50.0)
+    rd = GaussianRenderer(tile_size=spec.get("tile", 16), radius_min=0.01, radius_max=50.0)
     t0 = time.time()
     out = rd.render(RefCamera(cam), RefGaussians(m), settings)
     t_fwd = time.time() - t0
@@ -154,7 +162,8 @@ def run_oracle(spec, s, cam):
     leaf = {k: s[k].clone().requires_grad_(True) for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
     H, W = spec["H"], spec["W"]
     out = so.render_from_params(cam, leaf["xyz"], leaf["scaling"], leaf["rotation"], leaf["opacity"],
-                                leaf["features_dc"], torch.tensor(spec["bg"]), H, W, return_stats=True)
+                                leaf["features_dc"], torch.tensor(spec["bg"]), H, W, return_stats=True,
+                                tile_size=spec.get("tile", 16))
     out["viewspace_points"].retain_grad()
     loss = so.weighted_loss(out, so.loss_weights(H, W))
     loss.backward()
@@ -189,7 +198,8 @@ def make_case(name):
         rel(leaf["features_dc"].grad, ref["g_features_dc"]), rel(o["viewspace_points"].grad, ref["g_means2D"])))
     save = {"in_" + k: s[k].numpy() for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
     save.update({"cam_WV": cam.world_view.numpy(), "cam_fov": np.array([cam.fovx, cam.fovy], dtype=np.float64),
-                 "size_WH": np.array([spec["W"], spec["H"]]), "bg": np.array(spec["bg"], dtype=np.float32)})
+                 "size_WH": np.array([spec["W"], spec["H"]]), "bg": np.array(spec["bg"], dtype=np.float32),
+                 "tile_size": np.array(spec.get("tile", 16))})
     save.update({"ref_" + k: v.detach().numpy() for k, v in ref.items()})
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
 

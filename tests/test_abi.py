@@ -46,9 +46,9 @@ def test_argument_validation_without_gpu():
     _lib = import_module("mini-3d-gaussian-splatting_b200._lib")
     lib = _lib.load()
     cam = (ctypes.c_float * 20)()
-    rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, None, 0, 0, cam, 64, 64, 8, 0.01, 50.0,
+    rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, None, 0, 0, cam, 64, 64, 0, 0.01, 50.0,
                             None, None, None, None, None, None, None, None, None, None, None, None)
-    assert rc == -4 and b"tile_size" in lib.gs_last_error_string()       # GS_ERR_UNSUPPORTED
+    assert rc == -1 and b"tile_size" in lib.gs_last_error_string()       # GS_ERR_INVALID_ARGUMENT (any size >= 1 is accepted)
     rc = lib.gs_project_fwd(8, None, None, None, None, None, 0, None, 3, None, 0, 0, cam, 64, 64, 16, 0.01, 50.0,
                             None, None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1                                                       # GS_ERR_INVALID_ARGUMENT

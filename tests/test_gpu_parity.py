@@ -131,7 +131,10 @@ def test_golden_render_forward_and_gradients(name):
     d = util.load_golden(name)
     cam = util.golden_camera(d)
     params = util.golden_params(d)
-    out, grads, loss, rd, m = util.cuda_render_with_grads(cam, params, torch.tensor(d["bg"]))
+    T = util.golden_tile_size(d)
+    import gsplat_b200 as gb
+    out, grads, loss, rd, m = util.cuda_render_with_grads(cam, params, torch.tensor(d["bg"]),
+                                                          renderer=gb.GaussianRenderer(tile_size=T))
     # integer / index outputs: exact
     assert np.array_equal(out["visibility_filter"].cpu().numpy(), d["ref_vis"])
     assert np.array_equal(out["radii"].detach().cpu().numpy().astype(np.int64), d["ref_radii"].astype(np.int64))
@@ -142,7 +145,11 @@ def test_golden_render_forward_and_gradients(name):
     # images (vs the literal reference's pixels; the oracle supplies the per-pixel walk lengths)
     with torch.no_grad():
         o = so.render_from_params(cam, params["xyz"], params["scaling"], params["rotation"], params["opacity"],
-                                  params["features_dc"], torch.tensor(d["bg"]), cam.height, cam.width, return_stats=True)
+                                  params["features_dc"], torch.tensor(d["bg"]), cam.height, cam.width, return_stats=True,
+                                  tile_size=T)
+    # per-tile lists: the same entries in the same order, whatever the tile size
+    assert torch.equal(rd._last_debug["entry_ids"].cpu().long(), o["sort_ids"])
+    util.assert_same_ranges(rd._last_debug["tile_ranges"], o["tile_ranges"])
     ref = {k: torch.tensor(d["ref_" + k]) for k in ("image", "alpha", "depth")}
     rep = util.assert_images_close(out, ref, rd._last_debug["n_consumed"], o["n_consumed"], name)
     # gradients (a flipped pixel would perturb them; fixtures are small enough that none flips)
@@ -796,3 +803,32 @@ def test_truncated_lists_give_the_same_frame_as_complete_lists(cap):
         assert rd.list_cap > cap                            # the cap grew because tiles had to be completed
     else:
         assert rd.list_cap == cap
+
+
+@pytest.mark.parametrize("T", [4, 8, 12, 16, 20, 32, 48, 64])
+def test_any_tile_size_matches_the_oracle(T):
+    """renderer.py:24 takes any tile size.  The kernels composite 16x16 pixel blocks, ceil(T/16)^2 of them per tile; the
+    per-tile lists, the image and every gradient must follow the oracle run with the same tile size -- also through the
+    non-debug path (truncated lists for T <= 16, cached per-camera launch order on the second frame)."""
+    import gsplat_b200 as gb
+    s = so.scene_aniso(1200, 23)
+    s["scaling"] = s["scaling"] + math.log(3.0)
+    s["opacity"] = s["opacity"] + 1.0
+    cam = so.camera_orbit(2, 11, 150, 110)                 # ragged right / bottom tiles for every T above
+    bg = torch.tensor([0.15, 0.25, 0.1])
+    o_out, o_grads, _ = util.oracle_render_with_grads(cam, s, bg, tile_size=T)
+    rd = gb.GaussianRenderer(tile_size=T)
+    c_out, c_grads, _, _, m = util.cuda_render_with_grads(cam, s, bg, renderer=rd)
+    assert torch.equal(rd._last_debug["entry_ids"].cpu().long(), o_out["sort_ids"])
+    util.assert_same_ranges(rd._last_debug["tile_ranges"], o_out["tile_ranges"])
+    rep = util.assert_images_close(c_out, o_out, rd._last_debug["n_consumed"], o_out["n_consumed"], f"T={T}")
+    if rep["flips"] == 0:
+        for k in ("xyz", "scaling", "rotation", "opacity", "features_dc", "means2D"):
+            assert util.rel_err(c_grads[k], o_grads[k]) < GRAD_TOL, (T, k)
+    # the production path (no debug outputs): same pixels, twice (the second frame takes the cached launch order)
+    st = gb.RenderSettings(cam.height, cam.width, bg.cuda())
+    with torch.no_grad():
+        for _ in range(2):
+            plain = rd.render(util.cuda_camera(cam), m, st)
+            for k in ("image", "alpha", "depth"):
+                assert torch.equal(plain[k], c_out[k]), (T, k)

@@ -17,7 +17,8 @@ def test_oracle_matches_literal_reference_forward_and_grads(name):
         pytest.skip("fixture not generated")
     d = util.load_golden(name)
     cam = util.golden_camera(d)
-    out, grads, loss = util.oracle_render_with_grads(cam, util.golden_params(d), torch.tensor(d["bg"]))
+    out, grads, loss = util.oracle_render_with_grads(cam, util.golden_params(d), torch.tensor(d["bg"]),
+                                                     tile_size=util.golden_tile_size(d))
     # stage outputs: identical bits where the arithmetic is the same IEEE ops
     assert np.array_equal(out["viewspace_points"].detach().numpy().view(np.uint32), d["ref_means2D"].view(np.uint32))
     assert np.array_equal(out["depths"].detach().numpy().view(np.uint32), d["ref_depths"].view(np.uint32))

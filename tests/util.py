@@ -12,7 +12,11 @@ from oracle import splat_oracle as so
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PARAM_KEYS = ("xyz", "scaling", "rotation", "opacity", "features_dc")
 RENDER_CASES = ["aniso_n80_40x40_rot", "aniso_n120_48x40_orbit", "refinit_n300_64x64_saturating",
-                "aniso_n200_96x64_bigsplats"]
+                "aniso_n200_96x64_bigsplats", "aniso_n100_48x40_tile8", "aniso_n90_50x44_tile12", "aniso_n100_72x56_tile32"]
+
+
+def golden_tile_size(d) -> int:
+    return int(d["tile_size"]) if "tile_size" in d.files else 16
 
 
 def golden_available(name: str) -> bool:
@@ -49,12 +53,12 @@ def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
 
 
-def oracle_render_with_grads(cam: so.OracleCamera, params, bg, weights=None):
+def oracle_render_with_grads(cam: so.OracleCamera, params, bg, weights=None, tile_size: int = 16):
     """Oracle forward + autograd backward with the SURVEY 8d fixed-weight loss."""
     leaf = {k: params[k].clone().requires_grad_(True) for k in PARAM_KEYS}
     H, W = cam.height, cam.width
     out = so.render_from_params(cam, leaf["xyz"], leaf["scaling"], leaf["rotation"], leaf["opacity"], leaf["features_dc"],
-                                bg, H, W, return_stats=True)
+                                bg, H, W, return_stats=True, tile_size=tile_size)
     out["viewspace_points"].retain_grad()
     loss = so.weighted_loss(out, weights if weights is not None else so.loss_weights(H, W))
     loss.backward()
