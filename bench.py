@@ -476,6 +476,15 @@ def main():
                              "lane_instr_per_eval_at_roof": lane_roof / (evals / (kernels[top]["ms"] * 1e-3)),
                              "ncu_fma_pipe_active_pct": ncu_static.get("fma_pipe_active_pct"),
                              "ncu_issue_active_pct": ncu_static.get("issue_active_pct")}
+        slots = ncu_static.get("issue_slots_per_entry")
+        if slots:
+            # profiles/r2_issue_model.md: a packed FP32 instruction costs two issue slots, everything else one; the
+            # kernel's ceiling is its slot count per list entry x the entries each of the 592 schedulers walks
+            roofline["issue"].update({
+                "issue_slots_per_list_entry": slots,
+                "frac_of_issue_slot_roof": slots * E / (148 * 4 * kernels[top]["ms"] * 1e-3 * sm_clock * 1e6),
+                "model": "slots = 2 x packed FP32 instructions + 1 x every other instruction (tools/ubench_issue.cu, "
+                         "profiles/r2_issue_model.md); live: slots x consumed entries / (592 schedulers x kernel time x SM clock)"})
 
     if rank == 0:
         cpu = None
