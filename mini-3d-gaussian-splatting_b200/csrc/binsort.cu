@@ -387,7 +387,10 @@ __global__ void identity_order_kernel(int num_tiles, int32_t* __restrict__ tile_
 // for the chunk from which the tile's stored prefix is full.  The CTA that finishes last (ticket counter) then does the two
 // single-CTA steps on the totals all CTAs have published: the exclusive scan over tiles (tile_start / tile_ranges) and the
 // bucket sort of the tiles by list length (tile_order, heaviest first).
-constexpr int kTablesThreads = 256;
+#ifndef GS_TABLES_THREADS
+#define GS_TABLES_THREADS 256
+#endif
+constexpr int kTablesThreads = GS_TABLES_THREADS;
 constexpr int kOrderBuckets2 = 256;
 __global__ void __launch_bounds__(kTablesThreads)
 tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, const uint16_t* __restrict__ base16,

@@ -76,11 +76,22 @@ weighted_sum_kernel(WeightedTerms terms, LossWorkspace* ws, float* out) {
         const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
         long long done = 0;
         if (vec) {
-            for (long long i = (long long)blockIdx.x * kLossThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kLossThreads) {
+            // two independent 16-byte loads of each array in flight per thread and iteration
+            const long long stride = (long long)gridDim.x * kLossThreads;
+            float a2 = 0.f;
+            long long i = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+            for (; i + stride < n4; i += 2 * stride) {
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(x) + i), x1 = __ldg(reinterpret_cast<const float4*>(x) + i + stride);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + i), w1 = __ldg(reinterpret_cast<const float4*>(w) + i + stride);
+                a = fmaf(x0.x, w0.x, a); a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
+                a2 = fmaf(x1.x, w1.x, a2); a2 = fmaf(x1.y, w1.y, a2); a2 = fmaf(x1.z, w1.z, a2); a2 = fmaf(x1.w, w1.w, a2);
+            }
+            if (i < n4) {
                 const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
                 const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + i);
                 a = fmaf(xv.x, wv.x, a); a = fmaf(xv.y, wv.y, a); a = fmaf(xv.z, wv.z, a); a = fmaf(xv.w, wv.w, a);
             }
+            a += a2;
             done = n4 << 2;
         }
         for (long long i = done + (long long)blockIdx.x * kLossThreads + threadIdx.x; i < terms.n[k]; i += (long long)gridDim.x * kLossThreads)

@@ -349,15 +349,17 @@ class _RasterizeFn(torch.autograd.Function):
         if entry_ids is None:
             entry_ids = enqueue(bins.num_sorted, bins.D, None)
         entry_ids = entry_ids[:bins.D]
-        if cap:
-            bins.report_flagged(flag_count)         # asynchronous: the next frame doubles the cap if tiles were flagged
         bins.entry_ids, bins.tile_ranges = entry_ids, tile_ranges
         bins.renderer_consumed[(dev.index, W, H, T)] = tile_consumed
 
         ctx.side = None
+        if cap and side is None:
+            bins.report_flagged(flag_count)      # asynchronous: a later frame doubles the cap if tiles were flagged
         if side is not None:
-            ev[1].record(main)                   # tile_consumed is final
+            ev[1].record(main)                   # tile_consumed and the flag count are final
             side.wait_event(ev[1])
+            if cap:
+                bins.report_flagged(flag_count, tile_consumed, side)
             check(lib.gs_tile_order(slots, ptr(tile_consumed), None, ptr(bwd_order),
                                     ctypes.c_void_p(side.cuda_stream)), "gs_tile_order")
             ev[2].record(side)
@@ -435,22 +437,44 @@ class _FrameBins:
         self.fwd_order = renderer.fwd_tile_order
         self._renderer = renderer
         fb = renderer._cap_feedback.get(device.index)
-        if fb is not None and fb[1].query():          # the previous frame's flagged-tile count has arrived
-            if int(fb[0][0]) > 0 and renderer.list_cap:
-                renderer.list_cap = min(int(renderer.list_cap) * 2, 1 << 30)
+        if fb is not None and fb[1].query():          # an earlier frame's report {flagged tiles, deepest walk} has arrived
+            flagged, deepest = int(fb[0][0]), int(fb[0][1])
             renderer._cap_feedback[device.index] = None
+            if renderer.list_cap:
+                cap = int(renderer.list_cap)
+                if renderer.list_cap_auto and deepest >= 0:
+                    # follow what the tiles actually walk: the deepest walk of the recent frames (slowly forgotten) plus an
+                    # eighth, in steps of 64 entries -- any value is safe (a tile that needs more is completed and composited
+                    # again), a tight one saves scattered stores (8.4 M four-byte stores at cap 1 024 on config[1], whose
+                    # tiles never walk past entry 492)
+                    hi = max(deepest, int(renderer._deepest_walk.get(device.index, 0) * 0.98))
+                    renderer._deepest_walk[device.index] = hi
+                    target = max(128, -(-int(hi * 1.125 + 16) // 64) * 64)
+                    cap = target if not flagged else max(target, cap * 2)
+                elif flagged > 0:
+                    cap = cap * 2
+                renderer.list_cap = min(cap, 1 << 30)
         self.list_cap = renderer.list_cap
         self.num_sorted = self.D = self.num_vis = None
         self.entry_ids = self.tile_ranges = None
 
-    def report_flagged(self, flag_count):
+    def report_flagged(self, flag_count, tile_consumed=None, stream=None):
+        """Asynchronous report for the list-cap policy: {tiles the first pass flagged, deepest walk of any tile (-1 when
+        not measured)} copied to pinned memory on `stream` (the side stream when there is one: off the frame's critical
+        path) and read by a later frame once it has arrived."""
         slot = self._renderer._cap_pinned.get(self.device.index)
         if slot is None:
-            slot = self._renderer._cap_pinned[self.device.index] = torch.zeros(1, dtype=_I32).pin_memory()
+            slot = self._renderer._cap_pinned[self.device.index] = torch.zeros(2, dtype=_I32).pin_memory()
         if self._renderer._cap_feedback.get(self.device.index) is None:      # one report in flight at a time
-            slot.copy_(flag_count, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
+            stream = stream or torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(stream):
+                slot[0:1].copy_(flag_count, non_blocking=True)
+                if tile_consumed is not None and self._renderer.list_cap_auto:
+                    slot[1:2].copy_(tile_consumed.max().to(_I32).reshape(1), non_blocking=True)
+                else:
+                    slot[1] = -1
+                ev = torch.cuda.Event()
+                ev.record(stream)
             self._renderer._cap_feedback[self.device.index] = (slot, ev)
 
     def side_stream(self):
@@ -539,6 +563,8 @@ class GaussianRenderer:
         # truncated tile lists: entries stored / composited per tile before the completion path kicks in (0 = complete
         # lists).  Doubled automatically when a frame had to complete tiles.
         self.list_cap = 1024
+        self.list_cap_auto = True       # let the cap follow the deepest walk the tiles actually make (see _FrameBins)
+        self._deepest_walk: Dict[int, int] = {}
         # slab zero-fill and backward tile order on a side stream during the forward pass (see _RasterizeFn.forward)
         self.side_stream_prep = True
         self._side: Dict[int, tuple] = {}

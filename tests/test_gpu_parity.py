@@ -433,7 +433,7 @@ def test_full_size_truncated_lists_and_closed_blocks_equal_complete_lists(full_s
         tc_ref = full._last_debug["tile_consumed"].clone()
         rd = gb.GaussianRenderer()
         assert rd.list_cap == 1024
-        for it in range(2):                                  # exact sizes, then optimistic sizes
+        for it in range(4):                                  # exact sizes, then optimistic sizes, then the adapted list cap
             got = rd.render(cam, m, st)
             for k in ("image", "alpha", "depth"):
                 assert torch.equal(got[k], ref[k]), (it, k)
@@ -443,8 +443,12 @@ def test_full_size_truncated_lists_and_closed_blocks_equal_complete_lists(full_s
             assert torch.equal(rng, full._last_debug["tile_ranges"].long())
             t = int(torch.argmax(rng[:, 1] - rng[:, 0]))
             b = int(rng[t, 0])
-            assert int(rng[t, 1]) - b > 1024
-            assert torch.equal(rd._last_debug["entry_ids"][b:b + 1024], full._last_debug["entry_ids"][b:b + 1024])
+            used = int(rd.list_cap)                          # the cap this frame was binned with
+            assert int(rng[t, 1]) - b > 1024 >= used
+            assert torch.equal(rd._last_debug["entry_ids"][b:b + used], full._last_debug["entry_ids"][b:b + used])
+            torch.cuda.synchronize()                         # the frame's report {flagged tiles, deepest walk} has arrived
+        # the cap has followed the deepest walk of the tiles (492 entries on config[1]) and the frames stayed identical
+        assert 492 <= rd.list_cap < 1024, rd.list_cap
     for k in ("image", "alpha", "depth"):
         assert torch.equal(out_debug[k].detach(), ref[k]), k        # and the debug (tracking) kernel variant agrees
 
@@ -791,6 +795,7 @@ def test_truncated_lists_give_the_same_frame_as_complete_lists(cap):
     assert int(ref[1].max()) > 100                          # the scene does need more than the small caps
     rd = gb.GaussianRenderer()
     rd.list_cap = cap
+    rd.list_cap_auto = False                                # the doubling policy alone (the adaptive one: next test)
     for it in range(2):                                     # exact path, then the optimistic path
         got = frame(rd)
         for k in ("image", "alpha", "depth"):
