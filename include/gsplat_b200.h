@@ -254,7 +254,8 @@ int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size,
 int gs_tile_order(int32_t num_tiles, const int32_t* tile_consumed, const int32_t* tile_ranges, int32_t* tile_order,
                   void* stream);
 
-/* Backward of gs_raster_fwd.  g_image [3,H,W], g_alpha [1,H,W], g_depth [1,H,W] upstream.
+/* Backward of gs_raster_fwd.  g_image [3,H,W], g_alpha [1,H,W], g_depth [1,H,W] upstream; g_alpha and g_depth may be
+ * NULL when no gradient flows into that output (the reference's train step differentiates the image only).
  * Gradients are ACCUMULATED (atomic adds) into caller-zeroed g_means2d [n,2], g_conics [n,2,2],
  * g_depths [n], g_colors [n,3], g_opacities [n].
  * tile_order_scratch (optional, [num_tiles] int32): when given, the tiles are first bucketed by their exact

@@ -518,12 +518,14 @@ struct BwdAcc {
 
 // Backward arithmetic of one list entry for ONE pixel pair (kPk: packed or scalar FP32 instructions, same results).
 // kFirst: the lane's first pair of this entry initialises the partial sums instead of adding to zeros.
-template <bool kFast, bool kPk, bool kFirst>
+// kDepth: a depth gradient exists (otherwise gDs is identically zero: its term and the per-splat depth sum are dropped --
+// the reference's own train step differentiates the image only, optimizer.py:137-139).
+template <bool kFast, bool kPk, bool kFirst, bool kDepth>
 __device__ __forceinline__ void bwd_pair(float2 fpx, const EntryRow& row, float2& A, float2& R, float2 gCr, float2 gCg, float2 gCb,
                                          float2 gDs, float2 gA, float2 cr, float2 cg, float2 cb, float2 z, BwdAcc& acc) {
     PairEval ev;
     eval_pair<kFast, kPk>(fpx, row, A, ev);
-    const float2 v = fma2s<kPk>(gCr, cr, fma2s<kPk>(gCg, cg, fma2s<kPk>(gCb, cb, fma2s<kPk>(gDs, z, gA))));
+    const float2 v = fma2s<kPk>(gCr, cr, fma2s<kPk>(gCg, cg, fma2s<kPk>(gCb, cb, kDepth ? fma2s<kPk>(gDs, z, gA) : gA)));
     R = fma2s<kPk>(ev.contrib, v, R);
     A = add2s<kPk>(A, ev.contrib);
     // suffix / (1 - a); the terminating contributor has an empty suffix.  Otherwise
@@ -573,18 +575,18 @@ __device__ __forceinline__ void bwd_pair(float2 fpx, const EntryRow& row, float2
         acc.s_cr = mul2s<kPk>(ev.contrib, gCr);
         acc.s_cg = mul2s<kPk>(ev.contrib, gCg);
         acc.s_cb = mul2s<kPk>(ev.contrib, gCb);
-        acc.s_z = mul2s<kPk>(ev.contrib, gDs);
+        if (kDepth) acc.s_z = mul2s<kPk>(ev.contrib, gDs);
     } else {
         acc.s_cr = fma2s<kPk>(ev.contrib, gCr, acc.s_cr);
         acc.s_cg = fma2s<kPk>(ev.contrib, gCg, acc.s_cg);
         acc.s_cb = fma2s<kPk>(ev.contrib, gCb, acc.s_cb);
-        acc.s_z = fma2s<kPk>(ev.contrib, gDs, acc.s_z);
+        if (kDepth) acc.s_z = fma2s<kPk>(ev.contrib, gDs, acc.s_z);
     }
 }
 
 // Arithmetic of ONE list entry for this lane's 8 pixels; leaves the 10 per-lane partial sums in
 // rb[v * kRedStride + lane] (first half of the transpose reduction).  No barrier inside.
-template <bool kFast>
+template <bool kFast, bool kDepth>
 __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float fpy, const float2 (&fpx)[kPairs],
                                           float2 (&A)[kPairs], float2 (&R)[kPairs], const float2 (&gCr)[kPairs],
                                           const float2 (&gCg)[kPairs], const float2 (&gCb)[kPairs],
@@ -599,13 +601,14 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
     const float2 cr = bc2(r1.w), cg = bc2(r2.x), cb = bc2(r2.y), z = bc2(r1.z);
     BwdAcc acc;
     acc.s_h = bc2(0.f);
-    bwd_pair<kFast, (kPairs > GS_BWD_SCALAR_PAIRS), true>(fpx[0], row, A[0], R[0], gCr[0], gCg[0], gCb[0], gDs[0], gA[0], cr, cg, cb, z, acc);
+    if (!kDepth) acc.s_z = bc2(0.f);
+    bwd_pair<kFast, (kPairs > GS_BWD_SCALAR_PAIRS), true, kDepth>(fpx[0], row, A[0], R[0], gCr[0], gCg[0], gCb[0], gDs[0], gA[0], cr, cg, cb, z, acc);
 #pragma unroll
     for (int p = 1; p < kPairs; ++p) {
         if (p < kPairs - GS_BWD_SCALAR_PAIRS)
-            bwd_pair<kFast, true, false>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
+            bwd_pair<kFast, true, false, kDepth>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
         else
-            bwd_pair<kFast, false, false>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
+            bwd_pair<kFast, false, false, kDepth>(fpx[p], row, A[p], R[p], gCr[p], gCg[p], gCb[p], gDs[p], gA[p], cr, cg, cb, z, acc);
     }
     const float2 s_h = acc.s_h, s_x = acc.s_x, s_xx = acc.s_xx, s_op = acc.s_op, s_z = acc.s_z;
     const float2 s_cr = acc.s_cr, s_cg = acc.s_cg, s_cb = acc.s_cb;
@@ -634,7 +637,7 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
 // between -- so the scheduler overlaps one entry's shared-memory and MUFU latencies with the next
 // entry's independent work (measured: the barrier after every entry, not the atomics, was what bound
 // this kernel; profiles/r1_v5_raster.md) -- then one __syncwarp, then the second halves of their reductions.
-template <bool kFast>
+template <bool kFast, bool kDepth = true>
 __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane, float fpy, const float2 (&fpx)[kPairs],
                                           float2 (&A)[kPairs], float2 (&R)[kPairs], const float2 (&gCr)[kPairs],
                                           const float2 (&gCg)[kPairs], const float2 (&gCb)[kPairs],
@@ -642,7 +645,7 @@ __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane,
     for (int j = 0; j < cnt; j += kBwdGroup) {
 #pragma unroll
         for (int g = 0; g < kBwdGroup; ++g)
-            bwd_entry<kFast>(srec + (j + g) * 3, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA,
+            bwd_entry<kFast, kDepth>(srec + (j + g) * 3, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA,
                              out.red + g * (kRedVals * kRedStride));
         __syncwarp();
 #pragma unroll
@@ -651,6 +654,7 @@ __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane,
     }
 }
 
+template <bool kDepth>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, (GS_BWD_MINB + kWarpsPerCta - 1) / kWarpsPerCta)
 raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict__ entry_ids,
                   const int2* __restrict__ tile_ranges, const float4* __restrict__ rec,
@@ -721,10 +725,10 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
                 gr[h] = (pre_r >= 0.f && pre_r <= 1.f) ? g_image[q] : 0.f;
                 gg[h] = (pre_g >= 0.f && pre_g <= 1.f) ? g_image[plane + q] : 0.f;
                 gb[h] = (pre_b >= 0.f && pre_b <= 1.f) ? g_image[2 * plane + q] : 0.f;
-                const float gd = g_depth[q];
+                const float gd = kDepth ? g_depth[q] : 0.f;
                 const float den = add_rn(Af, 1e-6f);
                 gd_[h] = gd / den;
-                ga_[h] = g_alpha[q] - (gr[h] * bg0 + gg[h] * bg1 + gb[h] * bg2) - gd * st.w / (den * den);
+                ga_[h] = ((kDepth || g_alpha) ? g_alpha[q] : 0.f) - (gr[h] * bg0 + gg[h] * bg1 + gb[h] * bg2) - gd * st.w / (den * den);
                 Ti[h] = gr[h] * (st.x - bg0) + gg[h] * (st.y - bg1) + gb[h] * (st.z - bg2) + gd_[h] * st.w + ga_[h] * Af;
             }
         }
@@ -781,8 +785,8 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
         const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
         out.sid = sid[buf];
-        if (all_regular) bwd_batch<true>(srec[buf], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
-        else bwd_batch<false>(srec[buf], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
+        if (all_regular) bwd_batch<true, kDepth>(srec[buf], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
+        else bwd_batch<false, kDepth>(srec[buf], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
         id_cur = id_nxt;
         id_nxt = id_nn;
     }
@@ -810,8 +814,8 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
         const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
         out.sid = sid[0];
-        if (all_regular) bwd_batch<true>(srec[0], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
-        else bwd_batch<false>(srec[0], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
+        if (all_regular) bwd_batch<true, kDepth>(srec[0], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
+        else bwd_batch<false, kDepth>(srec[0], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
     }
 #endif
 }
@@ -915,7 +919,7 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
                              float* g_conics, float* g_depths, float* g_colors, float* g_opacities, void* stream) {
     const int rc = check_raster_args(img_w, img_h, tile_size, "gs_raster_bwd");
     if (rc != GS_OK) return rc;
-    GS_REQUIRE(tile_ranges && bg && alpha && pix_state && tile_consumed && g_image && g_alpha && g_depth && g_means2d &&
+    GS_REQUIRE(tile_ranges && bg && alpha && pix_state && tile_consumed && g_image && g_means2d &&
                    g_conics && g_depths && g_colors && g_opacities, "NULL array argument");
     DeviceGuard guard(alpha);
     const TileGeom geom = tile_geom(img_w, img_h, tile_size);
@@ -927,10 +931,18 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
         GS_CUDA_TRY(cudaGetLastError());
         count_launches(1);
     }
-    raster_bwd_kernel<<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
-        img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
-        (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, g_depth, g_means2d, g_conics,
-        g_depths, g_colors, g_opacities);
+    // g_alpha / g_depth may be NULL (no gradient flows into that output); without a depth gradient a leaner instantiation runs
+    GS_REQUIRE(g_depth == nullptr || g_alpha != nullptr, "g_depth without g_alpha: pass zeros for g_alpha");
+    if (g_depth)
+        raster_bwd_kernel<true><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
+            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
+            (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, g_depth, g_means2d, g_conics,
+            g_depths, g_colors, g_opacities);
+    else
+        raster_bwd_kernel<false><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
+            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
+            (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, nullptr, g_means2d, g_conics,
+            g_depths, g_colors, g_opacities);
     GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
     return GS_OK;

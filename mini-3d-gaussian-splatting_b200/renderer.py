@@ -400,12 +400,12 @@ class _RasterizeFn(torch.autograd.Function):
         g_colors = slab[7 * n:10 * n].view(n, 3)
         g_opac = slab[10 * n:11 * n]
         if ctx.any_visible and entry_ids.numel() > 0:
-            def dense(g, c):
-                if g is None:
-                    return torch.zeros((c, H, W), dtype=_F32, device=dev)
-                return g.contiguous()
-
-            gi, ga, gd = dense(g_image, 3), dense(g_alpha, 1), dense(g_depth, 1)
+            # outputs no gradient flows into: image needs dense zeros, alpha / depth are passed as NULL
+            gi = g_image.contiguous() if g_image is not None else torch.zeros((3, H, W), dtype=_F32, device=dev)
+            ga = g_alpha.contiguous() if g_alpha is not None else None
+            gd = g_depth.contiguous() if g_depth is not None else None
+            if gd is not None and ga is None:
+                ga = torch.zeros((1, H, W), dtype=_F32, device=dev)
             scratch = None
             if order is None:                    # heaviest tiles first (exact work): ordered inside gs_raster_bwd
                 order = scratch = torch.empty(tile_consumed.numel(), dtype=_I32, device=dev)

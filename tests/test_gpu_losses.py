@@ -99,3 +99,27 @@ def test_backward_preparation_on_the_side_stream_changes_nothing():
         assert torch.equal(res[0][0][k], res[1][0][k])
     for k in res[0][1]:
         assert util.rel_err(res[0][1][k], res[1][1][k]) < 1e-5, k       # atomics: summation order differs run to run
+
+
+@pytest.mark.parametrize("bg", [(0.0, 0.0, 0.0), (0.3, 0.1, 0.2)])
+def test_image_only_loss_takes_the_lean_backward_and_matches_oracle_autograd(bg):
+    """The reference's train step differentiates the image only (optimizer.py:137-139): alpha and depth then carry no
+    gradient, gs_raster_bwd gets NULL for them and runs its instantiation without the depth terms.  Gradients against
+    oracle autograd of the same L1 loss (a non-zero background keeps the dL/dA term alive)."""
+    s = so.scene_aniso(1500, 29)
+    s["scaling"] = s["scaling"] + math.log(3.0)
+    s["opacity"] = s["opacity"] + 1.0
+    cam = so.camera_orbit(4, 9, 144, 96)
+    bgt = torch.tensor(bg)
+    H, W = cam.height, cam.width
+    tgt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(3))
+    leaf = {k: s[k].clone().requires_grad_(True) for k in util.PARAM_KEYS}
+    o = so.render_from_params(cam, leaf["xyz"], leaf["scaling"], leaf["rotation"], leaf["opacity"], leaf["features_dc"], bgt, H, W)
+    (o["image"] - tgt).abs().mean().backward()
+    model = util.cuda_model_from_params(s)
+    rd = gb.GaussianRenderer()
+    out = rd.render(util.cuda_camera(cam), model, gb.RenderSettings(H, W, bgt.cuda()))
+    assert util.max_abs(out["image"], o["image"]) < util.IMG_TOL
+    losses.l1_loss(out["image"], tgt.cuda()).backward()
+    for k in util.PARAM_KEYS:
+        assert util.rel_err(getattr(model, "_" + k).grad, leaf[k].grad) < 1e-3, k

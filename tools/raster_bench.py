@@ -29,7 +29,10 @@ for r in range(reps + 2):
     if r == 2: timer.events.clear()
     out = rd.render(cam, model, st)
     out["viewspace_points"].retain_grad()
-    loss = (w[0] * out["image"]).sum() + (w[1] * out["alpha"]).sum() + 0.1 * (w[2] * out["depth"]).sum()
+    if os.environ.get("GS_LOSS") == "image":       # image-only gradient: the lean backward instantiation
+        loss = (w[0] * out["image"]).sum()
+    else:
+        loss = (w[0] * out["image"]).sum() + (w[1] * out["alpha"]).sum() + 0.1 * (w[2] * out["depth"]).sum()
     loss.backward()
     if chk is None:
         chk = (float(out["image"].double().sum()), float(out["alpha"].double().sum()), float(out["depth"].double().sum()),
