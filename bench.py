@@ -269,15 +269,22 @@ def main():
         # host once the next step has been enqueued (asynchronous logging) -- so the host never drains the GPU, but every
         # step's inputs cross H2D and every step's result crosses D2H and is consumed inside the timed region.
         k = e2e_state["k"]
+        if trace is not None:                                    # GS_BENCH_TRACE=1: where an end-to-end step spends its time
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record(torch.cuda.current_stream(dev))
+            t_host0 = time.perf_counter()
         if not e2e_state["primed"]:
             upload(k % 2)
             e2e_state["primed"] = True
         c = gb.Camera(WIDTH, HEIGHT, cam._FoVx, cam._FoVy, world_view=cam_wv_host)   # pose: 64 B, passed by value to the kernels
-        if k > 0:                                                # slot (k+1)%2 was last read by step k-1: wait for it ON THE GPU
-            copy_stream.wait_event(loss_ready[(k - 1) % 2])
-        upload((k + 1) % 2)                                      # next step's inputs
 
         def loss_after_upload(out, vid):
+            # The next step's inputs are sent from here -- after render() has read this frame's 24-byte counters back -- so that
+            # the 10 MB H2D copy never shares the PCIe link with that read-back, the one transfer the host waits for (measured
+            # at 8 GPUs: with the upload issued at the top of the step the GPU-side step was 2.04 ms instead of 1.83 ms).
+            if k > 0:                                            # slot (k+1)%2 was last read by step k-1: wait for it ON THE GPU
+                copy_stream.wait_event(loss_ready[(k - 1) % 2])
+            upload((k + 1) % 2)
             torch.cuda.current_stream(dev).wait_event(uploaded[k % 2])
             return loss_fn(out, stage[k % 2])
 
@@ -285,8 +292,15 @@ def main():
         loss_host[k % 2].copy_(res["losses"][0].reshape(1), non_blocking=True)
         loss_ready[k % 2].record(torch.cuda.current_stream(dev))
         e2e_state["k"] = k + 1
+        if trace is not None:
+            ev_b.record(torch.cuda.current_stream(dev))
+            t_host1 = time.perf_counter()
         if k > len(e2e_losses):
             collect(k - 1)                                       # host read of the previous step's result, this step already enqueued
+        if trace is not None:
+            trace.append((t_host0, t_host1, time.perf_counter(), ev_a, ev_b))
+
+    trace = [] if os.environ.get("GS_BENCH_TRACE") == "1" else None
 
     def finish_e2e():
         if e2e_state["k"] > len(e2e_losses):
@@ -388,6 +402,16 @@ def main():
     finish_e2e()                                         # the last step's loss is read inside the timed region too
     barrier()
     assert len(e2e_losses) == e2e_steps + 2 and all(np.isfinite(v) for v in e2e_losses)
+    if trace:
+        tr = trace[-e2e_steps:]
+        enq = [b - a for a, b, c_, _, _ in tr]
+        col = [c_ - b for a, b, c_, _, _ in tr]
+        period = [tr[i + 1][0] - tr[i][0] for i in range(len(tr) - 1)]
+        gpu = [ea.elapsed_time(eb) for _, _, _, ea, eb in tr]
+        gap = [tr[i][4].elapsed_time(tr[i + 1][3]) for i in range(len(tr) - 1)]
+        sys.stderr.write(f"[trace rank {rank}] per e2e step: host enqueue {np.mean(enq) * 1e3:.3f} ms (max {np.max(enq) * 1e3:.3f}), "
+                         f"collect {np.mean(col) * 1e3:.3f} ms, host period {np.mean(period) * 1e3:.3f} ms; GPU first-to-last kernel "
+                         f"{np.mean(gpu):.3f} ms (max {np.max(gpu):.3f}), GPU gap between steps {np.mean(gap):.3f} ms (max {np.max(gap):.3f})\n")
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
