@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -19,6 +20,14 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GSPLAT_B200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);

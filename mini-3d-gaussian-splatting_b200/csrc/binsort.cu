@@ -178,12 +178,17 @@ __device__ __forceinline__ int tile_of(int k, int origin, int w, unsigned inv, i
 __global__ void __launch_bounds__(32)
 chunk_walk_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int64_t* __restrict__ offsets,
                   const ushort4* __restrict__ tile_rect, int tiles_x, int row_tiles,
-                  uint8_t* __restrict__ local_pos, uint8_t* __restrict__ counts /* [chunks][row_tiles] */) {
+                  uint8_t* __restrict__ local_pos, uint8_t* __restrict__ counts /* [chunks][row_tiles] */,
+                  uint32_t* __restrict__ zero_words, int zero_count) {
     extern __shared__ uint32_t s_words[];
     uint8_t* s_cnt = reinterpret_cast<uint8_t*>(s_words);
     const int lane = threadIdx.x;
     const int64_t chunk = blockIdx.x;
     const int words = row_tiles >> 2;
+    // the tile-table launch's control block (ticket + closing chunks, < 1 KB) is cleared here, two launches ahead of its
+    // use, instead of by a memset between the kernels
+    if (chunk == 0)
+        for (int w = lane; w < zero_count; w += 32) zero_words[w] = 0u;
     int64_t num_sorted;
     if (!resolve_sizes(sizes, num_sorted)) return;
     const int64_t j_begin = chunk * kChunk;
@@ -246,6 +251,7 @@ column_prefix_kernel(BinSizes sizes, int row_tiles, const uint8_t* __restrict__ 
                      uint32_t* __restrict__ super_tot /* [supers][row_tiles] */) {
     __shared__ uint4 s_seg[32][33];
     const int lane = threadIdx.x, seg = threadIdx.y;
+    grid_dependency_wait();
     int64_t num_sorted;
     if (!resolve_sizes(sizes, num_sorted)) return;
     const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
@@ -399,6 +405,7 @@ tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, co
                    int32_t* __restrict__ tile_order, unsigned int* __restrict__ done_counter, int32_t* __restrict__ flag_count) {
     // truncated lists: this frame's count of tiles that need more than their stored prefix starts at zero (the
     // compositing pass that raises it is enqueued behind this launch)
+    grid_dependency_wait();
     if (flag_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0;
     __shared__ int s_cnt[kOrderBuckets2];
     __shared__ int s_off[kOrderBuckets2];
@@ -409,7 +416,10 @@ tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, co
     if (!resolve_sizes(sizes, num_sorted)) {
         // capacity overflow: no list is written (tile_ranges stay zero) and the caller repeats the stage with exact sizes, but
         // the compositing launch already enqueued behind this one still reads the order: give it a valid one
-        if (tile_order != nullptr && t < num_tiles) tile_order[t] = t;
+        if (t < num_tiles) {
+            reinterpret_cast<int2*>(ranges)[t] = make_int2(0, 0);
+            if (tile_order != nullptr) tile_order[t] = t;
+        }
         return;
     }
     const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
@@ -540,6 +550,7 @@ scatter_kernel(BinSizes sizes, const int32_t* __restrict__ sorted_ids, const int
                uint64_t* __restrict__ entry_keys, ListCap cap) {
     const int lane = threadIdx.x & 31;
     const int64_t j0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    grid_dependency_wait();
     int64_t num_sorted;
     if (!resolve_sizes(sizes, num_sorted)) return;
     if (j0 >= num_sorted) return;
@@ -974,10 +985,11 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
     GS_REQUIRE(d < (1ll << 31), "tile pairs must fit int32 positions");
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(tile_ranges);
-    GS_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st));
     const bool nothing = (counters_dev == nullptr && (d == 0 || num_sorted == 0)) ||
                          (counters_dev != nullptr && (d == 0 || n == 0));      // no pairs / no capacity: nothing can be written
     const bool counting_path = algo == GS_BIN_COUNTING || (algo == GS_BIN_AUTO && num_tiles <= kMaxCountingTiles);
+    // the flat counting sort writes every tile's range itself (zeros on a capacity overflow); every other way out starts from zeros
+    if (nothing || !counting_path) GS_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st));
     // flag_count (truncated lists): zeroed by the flat counting sort's tile-table launch; every other way out zeroes it here
     if (flag_count != nullptr && (nothing || !counting_path)) GS_CUDA_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
     if (nothing) {
@@ -1067,43 +1079,52 @@ extern "C" int gs_bin_sort(int64_t n, int64_t num_sorted, int64_t d, const int32
         uint8_t* local_pos = (uint8_t*)(wsc + C.local_pos);
         const size_t smem_walk = (size_t)C.row_tiles;
         const BinSizes sizes = {num_sorted, d, counters_dev};
-        if (smem_walk > 48 * 1024) GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_walk));
-        // one warp + row_tiles bytes per CTA: residency is bounded by shared memory, so ask for the largest carve-out
-        GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        chunk_walk_kernel<<<C.num_chunks, 32, smem_walk, st>>>(sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x,
-                                                              C.row_tiles, local_pos, counts);
-        GS_CUDA_TRY(cudaGetLastError());
-        column_prefix_kernel<<<dim3(C.row_tiles / kRowAlign, C.num_supers), dim3(32, 32), 0, st>>>(
-            sizes, C.row_tiles, counts, base16, super_tab);
-        GS_CUDA_TRY(cudaGetLastError());
         {
-            ListCap cap = {list_cap > 0 ? (uint32_t)list_cap : 0xFFFFFFFFu, nullptr, nullptr, nullptr, 0};
-            // super-chunk prefix, closing chunks (truncated lists), tile scan and the forward's tile order: one launch
-            unsigned int* ticket = (unsigned int*)(wsc + C.close_chunk);
-            int32_t* close_chunk = (int32_t*)(wsc + C.close_chunk + 256);
-            int blocks_x = 0;
-            size_t zero_bytes = 256;
-            const bool closing = list_cap > 0 && num_tiles % tiles_x == 0;
-            if (closing) {
-                const int tiles_y = num_tiles / tiles_x;
-                blocks_x = (tiles_x + kCloseBlk - 1) / kCloseBlk;
-                zero_bytes += (size_t)blocks_x * ((tiles_y + kCloseBlk - 1) / kCloseBlk) * sizeof(int32_t);
+            // function attributes once per device and size class, not per frame
+            static int walk_smem_set[64] = {0};
+            int dev_i = 0;
+            cudaGetDevice(&dev_i);
+            const int need = (int)smem_walk;
+            if (dev_i >= 0 && dev_i < 64 && walk_smem_set[dev_i] < need + 1) {
+                if (smem_walk > 48 * 1024)
+                    GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+                // one warp + row_tiles bytes per CTA: residency is bounded by shared memory, so ask for the largest carve-out
+                GS_CUDA_TRY(cudaFuncSetAttribute(chunk_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                walk_smem_set[dev_i] = need + 1;
             }
-            GS_CUDA_TRY(cudaMemsetAsync(ticket, 0, zero_bytes, st));
-            tile_tables_kernel<<<(C.row_tiles + kTablesThreads - 1) / kTablesThreads, kTablesThreads, 0, st>>>(
-                sizes, num_tiles, tiles_x, C.row_tiles, base16, super_tab, tile_total, tile_start, tile_ranges, cap.limit, blocks_x,
-                closing ? close_chunk : nullptr, tile_order, ticket, flag_count);
-            GS_CUDA_TRY(cudaGetLastError());
-            if (closing) {
-                cap.close_chunk = close_chunk;
-                cap.blocks_x = blocks_x;
-            }
-            const int64_t warps = (num_sorted + 31) / 32;
-            scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-                sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, local_pos, base16,
-                super_tab, tile_start, depth_keys, entry_ids, entry_keys, cap);
         }
+        ListCap cap = {list_cap > 0 ? (uint32_t)list_cap : 0xFFFFFFFFu, nullptr, nullptr, nullptr, 0};
+        // control block of the tile-table launch: ticket (256 B) + one closing chunk per 8x8-tile block
+        unsigned int* ticket = (unsigned int*)(wsc + C.close_chunk);
+        int32_t* close_chunk = (int32_t*)(wsc + C.close_chunk + 256);
+        int blocks_x = 0;
+        size_t zero_bytes = 256;
+        const bool closing = list_cap > 0 && num_tiles % tiles_x == 0;
+        if (closing) {
+            const int tiles_y = num_tiles / tiles_x;
+            blocks_x = (tiles_x + kCloseBlk - 1) / kCloseBlk;
+            zero_bytes += (size_t)blocks_x * ((tiles_y + kCloseBlk - 1) / kCloseBlk) * sizeof(int32_t);
+        }
+        chunk_walk_kernel<<<C.num_chunks, 32, smem_walk, st>>>(sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x,
+                                                              C.row_tiles, local_pos, counts, ticket, (int)(zero_bytes / 4));
         GS_CUDA_TRY(cudaGetLastError());
+        // the three launches below follow their predecessor directly (no memset in between): dispatched early (PDL)
+        GS_CUDA_TRY(launch_pdl(column_prefix_kernel, dim3(C.row_tiles / kRowAlign, C.num_supers), dim3(32, 32), 0, st,
+                               sizes, C.row_tiles, (const uint8_t*)counts, base16, super_tab));
+        // super-chunk prefix, closing chunks (truncated lists), tile scan and the forward's tile order: one launch
+        GS_CUDA_TRY(launch_pdl(tile_tables_kernel, dim3((C.row_tiles + kTablesThreads - 1) / kTablesThreads), dim3(kTablesThreads), 0, st,
+                               sizes, num_tiles, tiles_x, C.row_tiles, (const uint16_t*)base16, super_tab, tile_total, tile_start,
+                               tile_ranges, cap.limit, blocks_x, closing ? close_chunk : (int32_t*)nullptr, tile_order, ticket,
+                               flag_count));
+        if (closing) {
+            cap.close_chunk = close_chunk;
+            cap.blocks_x = blocks_x;
+        }
+        const int64_t warps = (num_sorted + 31) / 32;
+        GS_CUDA_TRY(launch_pdl(scatter_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st,
+                               sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, (const uint8_t*)local_pos,
+                               (const uint16_t*)base16, (const uint32_t*)super_tab, (const uint32_t*)tile_start, depth_keys, entry_ids,
+                               entry_keys, cap));
         count_launches(4);
         return GS_OK;
     }
@@ -1158,11 +1179,11 @@ extern "C" int gs_bin_complete(int64_t n, int64_t num_sorted, int64_t d, const i
     const char* wsc = (const char*)workspace;
     const BinSizes sizes = {num_sorted, d, counters_dev};
     const int64_t warps = (num_sorted + 31) / 32;
-    scatter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles, (const uint8_t*)(wsc + C.local_pos),
-        (const uint16_t*)(wsc + C.base16), (const uint32_t*)(wsc + C.super_tab), (const uint32_t*)(wsc + C.tile_start), nullptr,
-        entry_ids, nullptr, ListCap{(uint32_t)list_cap, tile_flags, flag_count, nullptr, 0});
-    GS_CUDA_TRY(cudaGetLastError());
+    GS_CUDA_TRY(launch_pdl(scatter_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+                           sizes, sorted_ids, offsets, (const ushort4*)tile_rect, tiles_x, C.row_tiles,
+                           (const uint8_t*)(wsc + C.local_pos), (const uint16_t*)(wsc + C.base16), (const uint32_t*)(wsc + C.super_tab),
+                           (const uint32_t*)(wsc + C.tile_start), (const uint32_t*)nullptr, entry_ids, (uint64_t*)nullptr,
+                           ListCap{(uint32_t)list_cap, tile_flags, flag_count, nullptr, 0}));
     count_launches(1);
     return GS_OK;
 }

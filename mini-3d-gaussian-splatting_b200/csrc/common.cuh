@@ -52,6 +52,31 @@ struct DeviceGuard {
     }
 };
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// A frame is a chain of ~12 dependent kernels; between two of them the GPU drains, the next grid is set up and its
+// first CTAs are dispatched (2-4 us per boundary in the steady-state timeline, profiles/r2_timeline_steady_state.txt).
+// Launched with programmatic stream serialization, the next kernel's CTAs are dispatched while the previous kernel's
+// last CTAs retire; every such kernel begins with grid_dependency_wait(), which returns once the previous kernel has
+// completed and its memory is visible, so nothing is read early.  GSPLAT_B200_PDL=0 launches the plain way.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- camera block passed by value to kernels ------------------------------------------------
 struct Camera {
     float r[9];

@@ -67,6 +67,7 @@ __device__ __forceinline__ void finish_loss(float thread_sum, float scale, LossW
 
 __global__ void __launch_bounds__(kLossThreads)
 weighted_sum_kernel(WeightedTerms terms, LossWorkspace* ws, float* out) {
+    grid_dependency_wait();                          // launched early (PDL) behind the compositing pass
     float acc = 0.f;
     for (int k = 0; k < terms.count; ++k) {
         const float* __restrict__ x = terms.x[k];
@@ -105,6 +106,7 @@ weighted_sum_kernel(WeightedTerms terms, LossWorkspace* ws, float* out) {
 __global__ void __launch_bounds__(kLossThreads)
 l1_loss_kernel(const float* __restrict__ x, const float* __restrict__ t, long long n, float grad_scale,
                float* __restrict__ grad, LossWorkspace* ws, float* out) {
+    grid_dependency_wait();
     float acc = 0.f;
     const float g = grad_scale / (float)n;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
@@ -157,8 +159,8 @@ extern "C" int gs_weighted_sum(int32_t num_terms, const float* const* x, const f
         total += terms.n[k];
     }
     DeviceGuard guard(out);
-    weighted_sum_kernel<<<loss_grid(total), kLossThreads, 0, (cudaStream_t)stream>>>(terms, (LossWorkspace*)workspace, out);
-    GS_CUDA_TRY(cudaGetLastError());
+    GS_CUDA_TRY(launch_pdl(weighted_sum_kernel, dim3(loss_grid(total)), dim3(kLossThreads), 0, (cudaStream_t)stream,
+                           terms, (LossWorkspace*)workspace, out));
     count_launches(1);
     return GS_OK;
 }
@@ -171,8 +173,8 @@ extern "C" int gs_l1_loss(const float* x, const float* target, int64_t n, float 
         return GS_ERR_WORKSPACE_TOO_SMALL;
     }
     DeviceGuard guard(out);
-    l1_loss_kernel<<<loss_grid(n), kLossThreads, 0, (cudaStream_t)stream>>>(x, target, n, grad_scale, grad, (LossWorkspace*)workspace, out);
-    GS_CUDA_TRY(cudaGetLastError());
+    GS_CUDA_TRY(launch_pdl(l1_loss_kernel, dim3(loss_grid(n)), dim3(kLossThreads), 0, (cudaStream_t)stream,
+                           x, target, (long long)n, grad_scale, grad, (LossWorkspace*)workspace, out));
     count_launches(1);
     return GS_OK;
 }

@@ -294,9 +294,12 @@ extern "C" int gs_peer_allreduce(const uint64_t* peer_ptrs_host, uint64_t multic
     const int64_t so = sum_offset / 4, sn = sum_count / 4, mo = max_offset / 4, mn = max_count / 4;
     if (multicast_ptr != 0) {
         GS_REQUIRE(multicast_ptr % 16 == 0, "multicast address must be 16-byte aligned");
-        int unroll = 4;
-        if (const char* e = getenv("GS_PEER_MC_UNROLL")) unroll = atoi(e);                  // tuning knob (tools/peer_pieces.py)
+        // 16 in-switch reductions in flight per thread, 4 CTAs per SM: 0.148 ms at 8 GPUs against 0.162 ms with 4 / 2
+        // (profiles/r2_multigpu.md); both are tuning knobs of tools/peer_pieces.py
+        int unroll = 16;
+        if (const char* e = getenv("GS_PEER_MC_UNROLL")) unroll = atoi(e);
         float* mcp = reinterpret_cast<float*>(multicast_ptr);
+        const dim3 grid((unsigned)(sms * (getenv("GS_PEER_GRID_MULT") ? mult : 4)));
         if (unroll >= 16) peer_allreduce_multimem_kernel<16><<<grid, block, 0, st>>>(mcp, world, rank, so, sn, mo, mn);
         else if (unroll >= 8) peer_allreduce_multimem_kernel<8><<<grid, block, 0, st>>>(mcp, world, rank, so, sn, mo, mn);
         else peer_allreduce_multimem_kernel<4><<<grid, block, 0, st>>>(mcp, world, rank, so, sn, mo, mn);

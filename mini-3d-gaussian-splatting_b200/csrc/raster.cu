@@ -339,6 +339,7 @@ raster_fwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
 
     // one warp per tile; warps never synchronise with each other, so a warp without a tile simply leaves
     const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
+    grid_dependency_wait();                                        // launched early (PDL): the binning's output is final from here
     if (slot >= geom.tiles_x * geom.tiles_y * geom.sub * geom.sub) return;
     const int slot_id = tile_order ? tile_order[slot] : slot;      // any permutation of the slots
     const int lane = threadIdx.x & 31;
@@ -672,6 +673,7 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
     float* red = red_all[threadIdx.x >> 5];
 
     const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
+    grid_dependency_wait();                                        // launched early (PDL)
     if (slot >= geom.tiles_x * geom.tiles_y * geom.sub * geom.sub) return;
     const int slot_id = tile_order ? tile_order[slot] : slot;      // any permutation of the slots
     const int lane = threadIdx.x & 31;
@@ -895,18 +897,18 @@ extern "C" int gs_raster_fwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     GS_REQUIRE(slots64 < (1ll << 31), "too many tiles");
     const int slots = (int)slots64;
     cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((unsigned)((slots + kWarpsPerCta - 1) / kWarpsPerCta)), block(32 * kWarpsPerCta);
     if (n_consumed) {
-        raster_fwd_kernel<true><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
-            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
-            n_consumed, tile_consumed);
+        GS_CUDA_TRY(launch_pdl(raster_fwd_kernel<true>, grid, block, 0, st,
+                               img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
+                               counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth,
+                               (float4*)pix_state, n_consumed, tile_consumed));
     } else {
-        raster_fwd_kernel<false><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
-            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
-            counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth, (float4*)pix_state,
-            nullptr, tile_consumed);
+        GS_CUDA_TRY(launch_pdl(raster_fwd_kernel<false>, grid, block, 0, st,
+                               img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, any_visible_host,
+                               counters_dev, tile_order, list_cap, tile_flags, flag_count, rerun, image, alpha, depth,
+                               (float4*)pix_state, (int32_t*)nullptr, tile_consumed));
     }
-    GS_CUDA_TRY(cudaGetLastError());
     count_launches(1);
     return GS_OK;
 }
@@ -933,17 +935,17 @@ extern "C" int gs_raster_bwd(int32_t img_w, int32_t img_h, int32_t tile_size, co
     }
     // g_alpha / g_depth may be NULL (no gradient flows into that output); without a depth gradient a leaner instantiation runs
     GS_REQUIRE(g_depth == nullptr || g_alpha != nullptr, "g_depth without g_alpha: pass zeros for g_alpha");
+    const dim3 grid((unsigned)((slots + kWarpsPerCta - 1) / kWarpsPerCta)), block(32 * kWarpsPerCta);
     if (g_depth)
-        raster_bwd_kernel<true><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
-            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
-            (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, g_depth, g_means2d, g_conics,
-            g_depths, g_colors, g_opacities);
+        GS_CUDA_TRY(launch_pdl(raster_bwd_kernel<true>, grid, block, 0, (cudaStream_t)stream,
+                               img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
+                               (const float4*)pix_state, tile_consumed, (const int32_t*)tile_order_scratch, g_image, g_alpha, g_depth,
+                               g_means2d, g_conics, g_depths, g_colors, g_opacities));
     else
-        raster_bwd_kernel<false><<<(slots + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(
-            img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
-            (const float4*)pix_state, tile_consumed, tile_order_scratch, g_image, g_alpha, nullptr, g_means2d, g_conics,
-            g_depths, g_colors, g_opacities);
-    GS_CUDA_TRY(cudaGetLastError());
+        GS_CUDA_TRY(launch_pdl(raster_bwd_kernel<false>, grid, block, 0, (cudaStream_t)stream,
+                               img_w, img_h, geom, entry_ids, (const int2*)tile_ranges, (const float4*)splat_rec, bg, alpha,
+                               (const float4*)pix_state, tile_consumed, (const int32_t*)tile_order_scratch, g_image, g_alpha,
+                               (const float*)nullptr, g_means2d, g_conics, g_depths, g_colors, g_opacities));
     count_launches(1);
     return GS_OK;
 }

@@ -109,10 +109,13 @@ class FlatGradBuffer:
         if len(ptrs) != dist.get_world_size(group) or any(p == 0 for p in ptrs):
             raise RuntimeError(f"symmetric memory rendezvous returned {ptrs}")
         import ctypes
-        # NVSwitch multicast (multimem.ld_reduce / multimem.st) is implemented and correct but measured no faster
-        # than plain peer loads/stores on this platform (profiles/r1_v5_multigpu.md): opt-in
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st: the switch reduces and replicates, ~36 % fewer bytes per link
+        # at 8 GPUs).  Measured (profiles/r2_multigpu.md): 0.148 ms against 0.187 ms (TMA) / 0.208 ms (loads/stores) at 8 GPUs
+        # with 16 reductions in flight per thread, but 0.19 against 0.108 ms at 2 GPUs, where it saves no bytes -- default
+        # from 8 ranks up; GSPLAT_B200_MULTICAST=0/1 overrides
         mc = 0
-        if os.environ.get("GSPLAT_B200_MULTICAST", "0") == "1":
+        mc_env = os.environ.get("GSPLAT_B200_MULTICAST", "")
+        if mc_env == "1" or (mc_env != "0" and dist.get_world_size(group) >= 8):
             try:
                 mc = int(handle.multicast_ptr or 0)
             except Exception:
