@@ -42,6 +42,25 @@ class RenderSettings:
     debug: bool = False
 
 
+def next_list_cap(cap: int, flagged: int, deepest: int, recent_deepest: int, auto: bool):
+    """List-cap policy of the truncated tile lists: (new cap, new memory of the deepest recent walk).
+
+    `flagged` tiles of an earlier frame needed more than their stored prefix (they were completed and composited again
+    inside that frame: any cap is safe); `deepest` is the deepest walk any tile made (-1 when not measured).
+    With `auto` the cap follows what the tiles actually walk -- the deepest walk of the recent frames, forgotten by 2 % per
+    report, plus an eighth, in steps of 64 entries and never below 128: a tight cap saves scattered stores (8.4 M
+    four-byte stores at cap 1 024 on config[1], whose tiles never walk past entry 492).  Without it, or when a frame had
+    to complete tiles although the target says the cap should have sufficed, the cap doubles."""
+    hi = recent_deepest
+    if auto and deepest >= 0:
+        hi = max(deepest, int(recent_deepest * 0.98))
+        target = max(128, -(-int(hi * 1.125 + 16) // 64) * 64)
+        cap = target if not flagged else max(target, cap * 2)
+    elif flagged > 0:
+        cap = cap * 2
+    return min(cap, 1 << 30), hi
+
+
 class _ViewMeta:
     """Per-call constants shared by forward and backward of the two Functions."""
 
@@ -441,19 +460,8 @@ class _FrameBins:
             flagged, deepest = int(fb[0][0]), int(fb[0][1])
             renderer._cap_feedback[device.index] = None
             if renderer.list_cap:
-                cap = int(renderer.list_cap)
-                if renderer.list_cap_auto and deepest >= 0:
-                    # follow what the tiles actually walk: the deepest walk of the recent frames (slowly forgotten) plus an
-                    # eighth, in steps of 64 entries -- any value is safe (a tile that needs more is completed and composited
-                    # again), a tight one saves scattered stores (8.4 M four-byte stores at cap 1 024 on config[1], whose
-                    # tiles never walk past entry 492)
-                    hi = max(deepest, int(renderer._deepest_walk.get(device.index, 0) * 0.98))
-                    renderer._deepest_walk[device.index] = hi
-                    target = max(128, -(-int(hi * 1.125 + 16) // 64) * 64)
-                    cap = target if not flagged else max(target, cap * 2)
-                elif flagged > 0:
-                    cap = cap * 2
-                renderer.list_cap = min(cap, 1 << 30)
+                renderer.list_cap, renderer._deepest_walk[device.index] = next_list_cap(
+                    int(renderer.list_cap), flagged, deepest, renderer._deepest_walk.get(device.index, 0), renderer.list_cap_auto)
         self.list_cap = renderer.list_cap
         self.num_sorted = self.D = self.num_vis = None
         self.entry_ids = self.tile_ranges = None

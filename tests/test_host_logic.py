@@ -75,3 +75,21 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["steps"] == 1 and d["ms_per_step"] * d["steps"] * 1e-3 < wall
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert "extrapolat" not in d["cpu_baseline"]["sample"].replace("nothing extrapolated", "")
+
+
+def test_list_cap_policy_follows_the_deepest_walk_and_doubles_when_tiles_were_flagged():
+    """Truncated tile lists (renderer.py next_list_cap): any cap is safe, the policy only trades stored entries against
+    completed tiles."""
+    from importlib import import_module
+    nxt = import_module("mini-3d-gaussian-splatting_b200.renderer").next_list_cap
+    assert nxt(1024, 0, 492, 0, True) == (576, 492)            # config[1]: 492 * 1.125 + 16 = 569.5 -> next multiple of 64
+    assert nxt(576, 0, 492, 492, True) == (576, 492)           # stable
+    cap, hi = nxt(576, 0, 100, 492, True)                      # an easy frame: the memory of the deep walk fades by 2 % only
+    assert (cap, hi) == (576, 482)
+    assert nxt(576, 3, 700, 492, True) == (1152, 700)          # tiles were flagged: at least double, whatever the target says
+    assert nxt(128, 5, 2000, 0, True) == (2304, 2000)          # ... or the target when it is larger
+    assert nxt(512, 0, 3, 0, True)[0] == 128                   # never below 128
+    assert nxt(512, 0, -1, 77, True) == (512, 77)              # nothing measured, nothing flagged: unchanged
+    assert nxt(512, 2, -1, 0, False) == (1024, 0)              # policy off: doubling only
+    assert nxt(512, 0, 300, 0, False) == (512, 0)
+    assert nxt(1 << 30, 1, -1, 0, False)[0] == 1 << 30         # bounded
