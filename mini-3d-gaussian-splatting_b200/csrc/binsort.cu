@@ -426,6 +426,10 @@ tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, co
     const int num_supers = (num_chunks + kSuper - 1) / kSuper;
     if (t < row_tiles) {
         uint32_t run = 0u;
+        // the super-chunk in which this tile's list reaches `limit` entries (truncated lists), noted while the prefixes are
+        // still in registers: the search for the closing chunk below then stays inside one super-chunk
+        int cross = -1;
+        uint32_t cross_base = 0u;
         int sidx = 0;
         for (; sidx + 8 <= num_supers; sidx += 8) {
             uint32_t v[8];
@@ -434,21 +438,30 @@ tile_tables_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, co
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 super_tab[(int64_t)(sidx + q) * row_tiles + t] = run;
+                if (cross < 0 && run + v[q] >= limit) { cross = sidx + q; cross_base = run; }
                 run += v[q];
             }
         }
         for (; sidx < num_supers; ++sidx) {
             const uint32_t v = super_tab[(int64_t)sidx * row_tiles + t];
             super_tab[(int64_t)sidx * row_tiles + t] = run;
+            if (cross < 0 && run + v >= limit) { cross = sidx; cross_base = run; }
             run += v;
         }
         tile_total[t] = run;
         if (close_chunk != nullptr && t < num_tiles) {
-            int lo = 0, hi = num_chunks;                      // first c in [0, num_chunks] with before(c, t) >= limit
-            if (run < limit) lo = num_chunks;                 // the whole list fits the stored prefix: never closed
+            // first c in [0, num_chunks] with before(c, t) = super prefix + in-super prefix >= limit; num_chunks: never closed
+            // (the whole list fits the stored prefix, or it fills up inside the last chunk).  before() is non-decreasing in c,
+            // below `limit` at the first chunk of super-chunk `cross` and at or above it at the first chunk of the next one:
+            // 8 dependent 2-byte loads instead of 12 pairs of loads over the whole column.
+            int lo = num_chunks, hi = num_chunks;
+            if (cross >= 0) {
+                lo = cross * kSuper;
+                hi = min(lo + kSuper, num_chunks);
+            }
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                const uint32_t before = super_tab[(int64_t)(mid / kSuper) * row_tiles + t] + (uint32_t)base16[(int64_t)mid * row_tiles + t];
+                const uint32_t before = cross_base + (uint32_t)base16[(int64_t)mid * row_tiles + t];
                 if (before >= limit) hi = mid; else lo = mid + 1;
             }
             const int ty = t / tiles_x, tx = t - ty * tiles_x;
