@@ -93,3 +93,22 @@ def test_list_cap_policy_follows_the_deepest_walk_and_doubles_when_tiles_were_fl
     assert nxt(512, 2, -1, 0, False) == (1024, 0)              # policy off: doubling only
     assert nxt(512, 0, 300, 0, False) == (512, 0)
     assert nxt(1 << 30, 1, -1, 0, False)[0] == 1 << 30         # bounded
+
+
+def test_fused_loss_object_behaves_like_a_scalar_loss_for_the_step_drivers():
+    """losses.FusedLoss (what the fused loss heads return) is consumed by multiview_step / train_step through
+    backward() / detach() / item(): its backward must route the precomputed gradients into the graph of its inputs."""
+    import torch
+    from importlib import import_module
+    FusedLoss = import_module("mini-3d-gaussian-splatting_b200.losses").FusedLoss
+    p = torch.arange(6, dtype=torch.float32, requires_grad=True)
+    img, alpha = (2.0 * p).reshape(2, 3), (p * p).sum().reshape(1)            # two "rendered outputs" of one graph
+    g_img, g_alpha = torch.full((2, 3), 0.5), torch.tensor([3.0])
+    loss = FusedLoss(torch.tensor(7.0), [img, alpha], [g_img, g_alpha])
+    assert loss.item() == 7.0 and float(loss.detach()) == 7.0 and float(loss) == 7.0
+    loss.backward()
+    assert torch.allclose(p.grad, 2.0 * 0.5 + 3.0 * 2.0 * p.detach())
+    # inputs that need no gradient are skipped, an empty loss is a no-op
+    FusedLoss(torch.tensor(0.0), [torch.zeros(3)], [torch.ones(3)]).backward()
+    with __import__("pytest").raises(RuntimeError):
+        import_module("mini-3d-gaussian-splatting_b200.losses").l1_loss(torch.zeros(3), torch.zeros(3))     # CPU tensors: no fallback
