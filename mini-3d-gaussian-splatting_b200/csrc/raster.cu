@@ -15,9 +15,10 @@
 //     pre-multiplied by -0.5*log2(e) when project_fwd packed the record; per batch of 32 entries a fast
 //     path drops both clamps of the reference (identities for records flagged `regular`) and folds the
 //     two skip rules into the weight itself (see eval_pair);
-//   * backward: each lane pre-sums its 8 pixels, then the 10 per-splat sums are reduced across the warp
-//     through a padded shared-memory transpose (10 STS + 3 LDS.128 per lane instead of 50 shuffles) and
-//     leave as ONE vector atomic instruction (lanes 0..9 -> 10 addresses);
+//   * backward: each lane pre-sums its 8 pixels, then 10 plain per-lane sums are reduced across the warp
+//     through a padded shared-memory transpose (10 STS + 3 LDS.128 per lane instead of 50 shuffles), the
+//     entry's conic / opacity factors are applied to the reduced sums by the lane that owns each output, and
+//     the eleven gradient values leave as ONE reduction instruction (lanes 0..10 -> 11 addresses);
 //   * tiles are taken longest-first (tile_order_kernel): the grids are ~3 waves of one-warp CTAs and the
 //     work per tile varies by 40 %, so raster order would leave full-size tiles in the last wave.
 //
@@ -38,6 +39,10 @@ namespace gs {
 #endif
 #ifndef GS_RASTER_WARPS
 #define GS_RASTER_WARPS 1              // tiles (= warps) per CTA; consecutive slots of the launch order, i.e. tiles of similar work
+#endif
+#ifndef GS_BWD_RAWSUMS
+#define GS_BWD_RAWSUMS 1               // backward: reduce the raw per-lane sums across the warp, apply the per-entry coefficients after
+                                       // (0: every lane forms the five conic / mean terms itself before the reduction; 838 vs 817 us)
 #endif
 #ifndef GS_BWD_GROUP
 #define GS_BWD_GROUP 2                 // list entries whose arithmetic runs between two warp barriers (backward)
@@ -485,12 +490,23 @@ struct BwdOut {
     float* red;               // [kRedVals][kRedStride] transpose buffer
     const float4* red_src;    // this lane's slice of it
     const int* sid;           // staged splat ids
+#if GS_BWD_RAWSUMS
+    // raw-sum reduction: the ten values crossing the warp are the lane's plain sums
+    //   0 Sx  1 dy*Sh  2 Sxx  3 dy*Sx  4 dy^2*Sh  5 S_opacity  6 z  7 r  8 g  9 b
+    // and the per-entry factors (conic, opacity, ln2, c) are applied once per entry AFTER the reduction, by the lane
+    // that owns the output: out = coef[ja] * T[ia] + coef[jb] * T[ib], T fetched from lanes ia / ib by shuffle and the
+    // entry's coefficient row {-2k q00', -k qs', -2k q11', c k, opacity factor, 1, 0, 0} (k = ln2, or ln2 * opacity on
+    // the general path) written to shared memory by the lane that staged the entry.
+    const float* coef;        // [kBatch][kCoefRow]
+    int ia, ib, ja, jb;
+#endif
 };
+constexpr int kCoefRow = 8;
 
 // Second half of the per-entry reduction: lanes 0..29 each add a third of one value's 32 partials
 // (12 + 12 + 8, read as float4), lanes v < 10 collect the three thirds and send ONE vector atomic.
 // Lanes 30/31 and the third float4 of lanes >= 20 read in-bounds scratch that is never used.
-__device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id, int lane) {
+__device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id, int lane, int entry) {
     const float4* src = out.red_src + buf * (kRedVals * kRedStride / 4);
     const float4 q0 = src[0], q1 = src[1], q2 = src[2];
     const float2 a01 = add2(make_float2(q0.x, q0.y), make_float2(q0.z, q0.w));
@@ -506,11 +522,34 @@ __device__ __forceinline__ void reduce_finish(const BwdOut& out, int buf, int id
     // reduction instruction serves all eleven addresses.  32-bit element offset: id * stride < 2^31 for every array the
     // ABI accepts.
     float total = s + s2 + s3;
+#if GS_BWD_RAWSUMS
+    (void)entry;
+    const float ta = __shfl_sync(0xffffffffu, total, out.ia), tb = __shfl_sync(0xffffffffu, total, out.ib);
+    const float* row = out.coef + entry * kCoefRow;
+    total = fmaf(row[out.jb], tb, row[out.ja] * ta);
+#else
+    (void)entry;
     const float q01 = __shfl_sync(0xffffffffu, total, 3);
     total = (lane == kRedVals) ? q01 : total;
+#endif
     float* dst = out.base + (unsigned)id * (unsigned)out.stride;
     if (lane <= kRedVals) atomicAdd(dst, total);
 }
+
+#if GS_BWD_RAWSUMS
+// Coefficient rows of one staged batch (see BwdOut); every lane writes the row of the entry it staged.
+__device__ __forceinline__ void stage_coef(bool all_regular, int lane, int cnt_pad, const float4* srec, float* coef) {
+    if (lane < cnt_pad) {
+        const float4 q0 = srec[lane * 3 + 0], q1 = srec[lane * 3 + 1];
+        const float inv_op = srec[lane * 3 + 2].z;
+        const float op = q1.y;
+        const float k = all_regular ? kLn2 : kLn2 * op;
+        float4* row = reinterpret_cast<float4*>(coef + lane * kCoefRow);
+        row[0] = make_float4(-2.f * k * q0.z, -k * q0.w, -2.f * k * q1.x, kNegHalfLog2e * k);
+        row[1] = make_float4(all_regular ? inv_op : (op > 0.f ? 1.f : 0.f), 1.f, 0.f, 0.f);
+    }
+}
+#endif
 
 // Per-lane partial sums of one list entry over the lane's pixels.
 struct BwdAcc {
@@ -613,6 +652,25 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
     }
     const float2 s_h = acc.s_h, s_x = acc.s_x, s_xx = acc.s_xx, s_op = acc.s_op, s_z = acc.s_z;
     const float2 s_cr = acc.s_cr, s_cg = acc.s_cg, s_cb = acc.s_cb;
+#if GS_BWD_RAWSUMS
+    // the lane's plain sums; conic / opacity / ln2 factors follow after the warp reduction (reduce_finish).  An entry staged
+    // with opacity 0 has exact-zero sums on the fast path and a zero opacity coefficient on the general one.
+    (void)op; (void)r0; (void)r1;
+    const float Sop_all = s_op.x + s_op.y;
+    const float Sh = kFast ? Sop_all : (s_h.x + s_h.y), Sx = s_x.x + s_x.y;
+    const float dySh = dy * Sh;
+    rb[0 * kRedStride + lane] = Sx;
+    rb[1 * kRedStride + lane] = dySh;
+    rb[2 * kRedStride + lane] = s_xx.x + s_xx.y;
+    rb[3 * kRedStride + lane] = dy * Sx;
+    rb[4 * kRedStride + lane] = dy * dySh;
+    rb[5 * kRedStride + lane] = Sop_all;
+    rb[6 * kRedStride + lane] = s_z.x + s_z.y;
+    rb[7 * kRedStride + lane] = s_cr.x + s_cr.y;
+    rb[8 * kRedStride + lane] = s_cg.x + s_cg.y;
+    rb[9 * kRedStride + lane] = s_cb.x + s_cb.y;
+}
+#else
     // an entry staged with opacity 0 (<= kTinyOpacity, or negative) is one the reference skips (a <= 0):
     // every sum below is then an exact zero except the opacity one, which is forced to zero
     // (fast path: the pixel sums hold a * dL/da with a = opacity * w, so the opacity is divided out here and dL/ds' needs ln2 only)
@@ -632,6 +690,7 @@ __device__ __forceinline__ void bwd_entry(const float4* srec_j, int lane, float 
     rb[8 * kRedStride + lane] = s_cg.x + s_cg.y;
     rb[9 * kRedStride + lane] = s_cb.x + s_cb.y;
 }
+#endif
 
 // One batch of the backward walk.  `cnt` is a multiple of kBwdGroup (the stager pads with null entries).
 // The entries are taken kBwdGroup at a time: their arithmetic runs back to back with no barrier in
@@ -650,7 +709,7 @@ __device__ __forceinline__ void bwd_batch(const float4* srec, int cnt, int lane,
                              out.red + g * (kRedVals * kRedStride));
         __syncwarp();
 #pragma unroll
-        for (int g = 0; g < kBwdGroup; ++g) reduce_finish(out, g, out.sid[j + g], lane);
+        for (int g = 0; g < kBwdGroup; ++g) reduce_finish(out, g, out.sid[j + g], lane, j + g);
         __syncwarp();
     }
 }
@@ -671,6 +730,10 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
     float4 (*srec)[kBatch * 3] = srec_all[threadIdx.x >> 5];
     int (*sid)[kBatch] = sid_all[threadIdx.x >> 5];
     float* red = red_all[threadIdx.x >> 5];
+#if GS_BWD_RAWSUMS
+    __shared__ __align__(16) float coef_all[kWarpsPerCta][kBatch * kCoefRow];
+    float* coef = coef_all[threadIdx.x >> 5];
+#endif
 
     const int slot = (int)blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5);
     grid_dependency_wait();                                        // launched early (PDL)
@@ -747,6 +810,15 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
     out.red = red;
     out.red_src = red_src;
     out.sid = sid[0];
+#if GS_BWD_RAWSUMS
+    out.coef = coef;
+    // which reduced sums (ia, ib) and which entries of the coefficient row (ja, jb) make this lane's output; lanes > 10
+    // compute a finite value nobody stores (jb = 6 is the row's constant 0)
+    out.ia = lane <= 9 ? lane : 3;                    // lane 10: Q10 = Q01's sum (value 3)
+    out.ib = lane == 0 ? 1 : (lane == 1 ? 0 : out.ia);
+    out.ja = lane == 0 ? 0 : lane == 1 ? 2 : (lane <= 4 || lane == 10) ? 3 : lane == 5 ? 4 : 5;
+    out.jb = lane <= 1 ? 1 : 6;
+#endif
 
     const int2 range = tile_ranges[tile];
     const int end = range.x + tile_consumed[slot_id];
@@ -786,6 +858,10 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
         }
         const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
+#if GS_BWD_RAWSUMS
+        stage_coef(all_regular, lane, cnt_pad, srec[buf], coef);
+        __syncwarp();
+#endif
         out.sid = sid[buf];
         if (all_regular) bwd_batch<true, kDepth>(srec[buf], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
         else bwd_batch<false, kDepth>(srec[buf], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
@@ -815,6 +891,10 @@ raster_bwd_kernel(int img_w, int img_h, TileGeom geom, const int32_t* __restrict
         }
         const bool all_regular = __all_sync(0xffffffffu, regular);
         __syncwarp();
+#if GS_BWD_RAWSUMS
+        stage_coef(all_regular, lane, cnt_pad, srec[0], coef);
+        __syncwarp();
+#endif
         out.sid = sid[0];
         if (all_regular) bwd_batch<true, kDepth>(srec[0], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
         else bwd_batch<false, kDepth>(srec[0], cnt_pad, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);

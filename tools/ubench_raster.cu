@@ -95,6 +95,16 @@ __global__ void __launch_bounds__(32, GS_BWD_MINB) bwd_loop_kernel(int rounds, i
     out.red = red;
     out.red_src = reinterpret_cast<const float4*>(&red[red_v * kRedStride + red_g * 12]);
     out.sid = sid;
+#if GS_BWD_RAWSUMS
+    __shared__ __align__(16) float coef[kBatch * kCoefRow];
+    stage_coef(true, lane, kBatch, srec, coef);
+    __syncwarp();
+    out.coef = coef;
+    out.ia = lane <= 9 ? lane : 3;
+    out.ib = lane == 0 ? 1 : (lane == 1 ? 0 : out.ia);
+    out.ja = lane == 0 ? 0 : lane == 1 ? 2 : (lane <= 4 || lane == 10) ? 3 : lane == 5 ? 4 : 5;
+    out.jb = lane <= 1 ? 1 : 6;
+#endif
     const long long t0 = clock64();
     for (int r = 0; r < rounds; ++r) bwd_batch<true>(srec, kBatch, lane, fpy, fpx, A, R, gCr, gCg, gCb, gDs, gA, out);
     const long long t1 = clock64();
