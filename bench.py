@@ -13,12 +13,15 @@ backward), and for N > 1 the gradient/statistics all-reduce.  Prints ONE JSON li
 
   value      frames/s, whole job, inputs resident in HBM, timed on the device with CUDA events per
              step (L2 flushed before every step, max over ranks)
-  e2e        frames/s (wall clock) through the public API with every step's host inputs (camera + loss
-             weights, pinned) copied H2D one step ahead on a copy stream and every step's loss copied D2H
-             (pinned, non-blocking) and read by the host one step later, all inside the timed region
+  e2e        frames/s (wall clock, max(steps, 60) steps) through the public API with every step's host inputs
+             (camera + the loss-weight planes as 8-bit fixed point, 10.4 MB, pinned) copied H2D one step ahead on a
+             copy stream -- issued after the frame's counter read-back, dequantised there -- and every step's loss
+             copied D2H (pinned, non-blocking) and read by the host one step later, all inside the timed region
   roofline   the dominant kernel (largest share of the step): algorithmic bytes / its CUDA-event
-             duration vs the measured HBM peak of MEASURED_PEAKS.json; `kernels` lists all stages
-  cpu_baseline  the oracle's plain-C port of the same path on the host cores (bounded sample)
+             duration vs the measured HBM peak of MEASURED_PEAKS.json, plus `issue`: its fraction of the
+             issue-slot roof that actually bounds it (profiles/r2_issue_model.md); `kernels` lists all stages
+  cpu_baseline  the oracle's plain-C port of the same path on all host cores: one whole frame, nothing sampled
+  GS_BENCH_TRACE=1  prints (stderr) where an end-to-end step spends its time: host enqueue, GPU span
 """
 from __future__ import annotations
 
