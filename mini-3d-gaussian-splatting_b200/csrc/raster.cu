@@ -32,7 +32,7 @@
 namespace gs {
 
 #ifndef GS_FWD_MINB
-#define GS_FWD_MINB 1                  // min resident warps(=CTAs)/SM asked of ptxas for the forward kernel
+#define GS_FWD_MINB 18                 // resident one-warp CTAs per SM asked of ptxas for the forward kernel: 96 registers instead of 111, no spills (325 -> 321 us)
 #endif
 #ifndef GS_BWD_MINB
 #define GS_BWD_MINB 16
