@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--splats", type=int, default=N_SPLATS, help="debug only; the reported metric is defined at 1M")
+    ap.add_argument("--sh-degree", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="0 (default) = the reference's colour, sigmoid of the DC row (renderer.py:88-92); 1..3 = the opt-in "
+                         "view-dependent extension, which also reads and differentiates _features_rest [N,15,3]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, emit)
@@ -221,7 +224,7 @@ def main():
 
     model = gb.GaussianModel(device=dev)
     model.create_from_random(n, 1.0, seed=0)          # identical scene on every rank (replicated Gaussians)
-    rd = gb.GaussianRenderer()
+    rd = gb.GaussianRenderer(sh_degree=args.sh_degree)
     settings = gb.RenderSettings(HEIGHT, WIDTH, torch.zeros(3, device=dev))
     # one view per rank per step: rank r renders orbit view r of `world` (C0 when single-GPU)
     cam = gb.Camera.look_at_origin_c0(WIDTH, HEIGHT) if world == 1 else gb.Camera.orbit(rank, world, WIDTH, HEIGHT)
@@ -471,6 +474,9 @@ def main():
         "raster_bwd": T * 12 + E * 52 + E * 44 + P * 40,
         "project_bwd": n * (56 + 44 + 56 + 17),              # parameters, incoming gradients, outgoing gradients, statistics
     }
+    if args.sh_degree > 0:                                   # the 15 higher-order rows: read forward and backward, gradient written
+        alg["project_fwd"] += n * 180
+        alg["project_bwd"] += n * 360
     hbm_peak, peak_src = measured_peaks()
     kernels = {k: {"ms": per[k], "alg_bytes": alg[k], "gbs": alg[k] / (per[k] * 1e-3) / 1e9,
                    "frac_of_hbm_peak": alg[k] / (per[k] * 1e-3) / 1e9 / hbm_peak, "share_of_step": per[k] / ms_per_step}
@@ -527,6 +533,11 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "views_per_gpu_per_step": 1, "splats": n, "resolution": [WIDTH, HEIGHT],
+                       "sh_degree": args.sh_degree,
+                       "colour": ("sigmoid of the DC feature row, as the reference renders it (renderer.py:88-92: the model stores "
+                                  "15 higher-order rows, all zero after create_from_random, and render() never reads them)"
+                                  if args.sh_degree == 0 else
+                                  f"view-dependent real-SH colour of degree {args.sh_degree} (extension; --sh-degree)"),
                        "visible": V, "tile_pairs_D": D, "consumed_entries_E": E,
                        "l2": "flushed before every timed step (256 MiB memset); per-step working set > L2",
                        "renderer": {"binning": "flat counting sort, optimistic sizes, tile lists truncated to their first "
