@@ -17,3 +17,4 @@ try:
 except Exception as e: print('no bench line', e)
 PY
 done
+nvidia-smi topo -m > gpurun_out/topo_${N}gpu_$TAG.txt 2>&1
