@@ -97,7 +97,9 @@ entry_keys_kernel(int64_t d, const uint32_t* __restrict__ sorted_tile_keys, cons
 //                           chunk (uint8, written coalesced), counts[chunk][t] (uint8 row) at the end
 //   2. column_prefix_kernel base16[chunk][t] = pairs of tile t in earlier chunks of the same super-chunk
 //                           (uint16), super_tot[super][t]
-//   3. super_prefix_kernel + tile_scan_kernel   super_tab -> exclusive prefix over supers; tile_start / tile_ranges
+//   3. tile_tables_kernel   super_tab -> exclusive prefix over supers, the tiles' totals, the chunk from which each
+//                           8x8-tile block is closed (truncated lists), then -- last CTA to finish -- tile_start /
+//                           tile_ranges and the forward's tile order.  (tile_scan_kernel alone serves the blocked algo.)
 //   4. scatter_kernel       fully parallel, in rank order (so the 4-byte stores of neighbouring list
 //                           entries reach L2 close together and merge before they are written back):
 //                           entry_ids[tile_start + super_tab + base16 + local] = id
@@ -284,37 +286,8 @@ column_prefix_kernel(BinSizes sizes, int row_tiles, const uint8_t* __restrict__ 
     if (seg == 31) *reinterpret_cast<uint4*>(super_tot + (int64_t)sup * row_tiles + t4) = run;
 }
 
-// 3a. per tile: exclusive prefix over the super-chunks (in place) and the tile's total.  One thread per
-// tile, coalesced across the block; the loads of a column are independent and stay in flight together.
-__global__ void __launch_bounds__(128)
-super_prefix_kernel(BinSizes sizes, int row_tiles, uint32_t* __restrict__ super_tab, uint32_t* __restrict__ tile_total) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= row_tiles) return;
-    int64_t num_sorted;
-    if (!resolve_sizes(sizes, num_sorted)) return;
-    const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
-    const int num_supers = (num_chunks + kSuper - 1) / kSuper;
-    uint32_t run = 0u;
-    int s = 0;
-    for (; s + 8 <= num_supers; s += 8) {
-        uint32_t v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = super_tab[(int64_t)(s + q) * row_tiles + t];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            super_tab[(int64_t)(s + q) * row_tiles + t] = run;
-            run += v[q];
-        }
-    }
-    for (; s < num_supers; ++s) {
-        const uint32_t v = super_tab[(int64_t)s * row_tiles + t];
-        super_tab[(int64_t)s * row_tiles + t] = run;
-        run += v;
-    }
-    tile_total[t] = run;
-}
-
-// 3b. exclusive scan over tiles -> tile_start and tile_ranges [begin,end).  One block of 1024 threads.
+// exclusive scan over tiles -> tile_start and tile_ranges [begin,end).  One block of 1024 threads (blocked algo; the
+// flat counting sort does the same scan inside tile_tables_kernel).
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(BinSizes sizes, int num_tiles, const uint32_t* __restrict__ tile_total, uint32_t* __restrict__ tile_start,
                  int32_t* __restrict__ ranges) {
@@ -359,38 +332,18 @@ tile_scan_kernel(BinSizes sizes, int num_tiles, const uint32_t* __restrict__ til
     }
 }
 
-// 3c. truncated lists: from which chunk on is a tile's stored prefix full?  before(c, t) = super_tab + base16 is
-// non-decreasing in the chunk index c, so one binary search per tile finds the first chunk with before >= limit
-// (num_chunks if the tile's list is shorter than the limit); the maximum over the tiles of an 8x8 block is the chunk
-// from which the whole block is closed.  Depth ranks are sorted, so on config[1] ~60 % of the ranks meet closed
-// blocks only and the scatter drops them after reading their rectangle.
-__global__ void __launch_bounds__(256)
-close_chunk_kernel(BinSizes sizes, int num_tiles, int tiles_x, int row_tiles, const uint16_t* __restrict__ base16,
-                   const uint32_t* __restrict__ super_tab, uint32_t limit, int blocks_x, int32_t* __restrict__ close_chunk) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_tiles) return;
-    int64_t num_sorted;
-    if (!resolve_sizes(sizes, num_sorted)) return;
-    const int num_chunks = (int)((num_sorted + kChunk - 1) / kChunk);
-    int lo = 0, hi = num_chunks;                      // first c in [0, num_chunks] with before(c, t) >= limit
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const uint32_t before = super_tab[(int64_t)(mid / kSuper) * row_tiles + t] + (uint32_t)base16[(int64_t)mid * row_tiles + t];
-        if (before >= limit) hi = mid; else lo = mid + 1;
-    }
-    const int ty = t / tiles_x, tx = t - ty * tiles_x;
-    atomicMax(&close_chunk[(ty / kCloseBlk) * blocks_x + tx / kCloseBlk], lo);
-}
-
 __global__ void identity_order_kernel(int num_tiles, int32_t* __restrict__ tile_order) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < num_tiles) tile_order[t] = t;
 }
 
-// 3 (fused).  super_prefix + close_chunk + tile_scan + the forward's longest-first tile order in ONE launch.
+// 3.  Super-chunk prefix + closing chunks + tile scan + the forward's longest-first tile order in ONE launch.
 // These were four latency-bound launches of 6-10 us each (a fifth of gs_bin_sort).  Phase 1 runs on every CTA, one thread
-// per tile: exclusive prefix over the super-chunks (in place), the tile's total, and -- truncated lists -- the binary search
-// for the chunk from which the tile's stored prefix is full.  The CTA that finishes last (ticket counter) then does the two
+// per tile: exclusive prefix over the super-chunks (in place), the tile's total, and -- truncated lists -- the chunk from
+// which the tile's stored prefix is full: before(c, t) = super_tab + base16 is non-decreasing in the chunk index c, so a
+// binary search per tile finds the first chunk with before >= limit (num_chunks if the list is shorter than the limit); the
+// maximum over the tiles of an 8x8 block is the chunk from which the whole block is closed.  Depth ranks are sorted, so on
+// config[1] ~60 % of the ranks meet closed blocks only and the scatter drops them after reading their rectangle.  The CTA that finishes last (ticket counter) then does the two
 // single-CTA steps on the totals all CTAs have published: the exclusive scan over tiles (tile_start / tile_ranges) and the
 // bucket sort of the tiles by list length (tile_order, heaviest first).
 #ifndef GS_TABLES_THREADS
