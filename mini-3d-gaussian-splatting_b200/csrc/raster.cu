@@ -3,10 +3,11 @@
 // Reference semantics: the pixel loop and epilogue of GaussianRenderer._tile_rasterization,
 // src/core/renderer.py:300-367.
 //
-// Both kernels are bound by the FP32 FMA pipe, not by HBM (ncu, profiles/r1_v6_*: DRAM < 2 %, FMA pipe
-// 61-65 % busy with math_pipe_throttle the top stall): a tile saturates after a few hundred of its
-// thousands of list entries, so ~0.3 GB moves while ~6e8 pixel x splat evaluations execute.  The design
-// therefore minimises instructions -- FMA-pipe instructions first -- per evaluation:
+// Both kernels are bound by instruction issue, not by HBM (ncu: DRAM < 7 % of peak; a tile saturates after a few
+// hundred of its thousands of list entries, so ~0.3 GB moves while ~6e8 pixel x splat evaluations execute).  The
+// roof is a count of issue slots -- a packed FP32 instruction costs two, everything else one -- measured in
+// profiles/r2_issue_model.md (tools/ubench_issue.cu): 122.5 slots per list entry forward, 307 backward, the kernels
+// at 0.88 / 0.84 of it.  The design therefore minimises issue slots per evaluation:
 //   * one warp per tile, each lane owns a 1x8 pixel strip (16 rows x 2 strips) kept as 4 packed fp32 pairs
 //     (FFMA2 / FMUL2 / FADD2): the per-entry work (shared-memory broadcast of the 48-byte record, the dy
 //     terms, loop control) is amortised over 8 evaluations, 4 independent dependency chains hide FP32/MUFU
@@ -74,9 +75,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// Blackwell packed fp32: one issue slot, two IEEE-rounded fp32 results (FFMA2 / FADD2 / FMUL2).
-// Each lane keeps its 8 pixels as 4 (even, odd) pairs so the per-pixel arithmetic issues at half
-// the instruction count -- the kernels are issue-bound, so this is the sm_100-specific lever.
+// Blackwell packed fp32: one instruction, two IEEE-rounded fp32 results (FFMA2 / FADD2 / FMUL2).  Each lane keeps its
+// 8 pixels as 4 (even, odd) pairs.  Measured (profiles/r2_issue_model.md): a packed instruction holds its scheduler for
+// two cycles, so packing buys no FP32 throughput; what it buys is half the instruction count around the arithmetic
+// (operand moves, predicates stay per pair) and the registers of one pair per two pixels -- scalar pairs measured
+// slower (profiles/r2_experiments.md: 367 -> 389 us forward with two of the four pairs scalar).
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
