@@ -3,14 +3,17 @@ reduction per step.
 
 The reference has no multi-GPU code; this is the caller the render path gets when a batch of
 cameras is split over the GPUs of one box.  Each rank renders its views through the ordinary
-single-GPU pipeline.  Parameter gradients accumulate -- through autograd's in-place
-accumulation -- directly into views of ONE flat fp32 buffer laid out as
+single-GPU pipeline.  Parameter gradients and densification statistics accumulate directly into ONE
+flat fp32 buffer laid out as
 
-    [ xyz 3N | features_dc 3N | scaling 3N | rotation 4N | opacity N | grad-norm sum N | visible count N ]
+    [ xyz 3N | features_dc 3N | scaling 3N | rotation 4N | opacity N | grad-norm sum N | visible count N ][ max radii N ]
 
-so the exchange is a single SUM all-reduce (64 B/splat) plus a MAX all-reduce of the screen
-radii, with no packing kernel.  Works with any torch.distributed backend: NCCL over NVLink on the
-GPUs, gloo in the CPU tests (where a stand-in renderer supplies the per-view outputs).
+(every segment 16-byte aligned) -- written by gs_project_bwd itself when the renderer is the B200 one
+(`GaussianRenderer.accumulate_into`), through autograd's in-place `.grad` accumulation otherwise -- so the
+exchange is one SUM over the first 16 floats per splat plus one MAX over the screen radii, with no packing
+kernel: a single peer-memory kernel over NVLink on a CUDA process group (`gs_peer_allreduce`), two
+all-reduces on any other torch.distributed backend (gloo in the CPU tests, where a stand-in renderer
+supplies the per-view outputs).
 """
 from __future__ import annotations
 
@@ -121,7 +124,7 @@ class FlatGradBuffer:
             except Exception:
                 mc = 0
         # GS_PEER_TMA: bulk asynchronous copies (TMA) instead of per-thread loads/stores.  Measured on this pool's boxes
-        # (profiles/r2_multigpu.md): identical at 2 GPUs (both sit at the ~315 GB/s per-direction NVLink rate), 10 %
+        # (profiles/r2_multigpu.md): identical at 2 GPUs (both sit at the links' practical rate, ~630 GB/s per direction), 10 %
         # faster at 8 (0.188 vs 0.210 ms) -- default from 4 ranks up; GSPLAT_B200_PEER_TMA=0/1 overrides
         tma_env = os.environ.get("GSPLAT_B200_PEER_TMA", "")
         flags = int(tma_env == "1") if tma_env in ("0", "1") else int(len(ptrs) >= 4)
