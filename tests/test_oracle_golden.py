@@ -148,3 +148,28 @@ def test_sh_basis_of_the_oracle_is_orthonormal_on_the_sphere():
     assert torch.allclose(gram, torch.eye(16, dtype=torch.float64), atol=1e-9)
     for deg, terms in ((1, 3), (2, 8)):                            # lower degrees are prefixes of the same basis
         assert torch.equal(so.sh_basis(deg, d), so.sh_basis(3, d)[:, :terms])
+
+
+def test_sh_basis_of_the_oracle_equals_scipy_spherical_harmonics():
+    """Third-party pin of the SH extension (the reference's own evaluator is a stub, math_utils.py:44-49): the
+    oracle's Y_1..Y_15 are the real combinations of scipy.special.sph_harm_y (complex harmonics, Condon-Shortley phase
+    kept) -- sqrt(2) Im Y_l^|m| for m < 0, Y_l^0, sqrt(2) Re Y_l^m for m > 0 -- in the order m = -l..l within each
+    degree, which is the convention of the original 3DGS code the north star names."""
+    import numpy as np
+    import torch
+    scipy_special = pytest.importorskip("scipy.special")
+    if not hasattr(scipy_special, "sph_harm_y"):
+        pytest.skip("scipy.special.sph_harm_y needs scipy >= 1.15")
+    from oracle import splat_oracle as so
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=(2000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    theta, phi = np.arccos(d[:, 2]), np.arctan2(d[:, 1], d[:, 0])     # polar, azimuth
+    cols = []
+    for l in (1, 2, 3):
+        for m in range(-l, l + 1):
+            Y = scipy_special.sph_harm_y(l, abs(m), theta, phi)
+            cols.append(Y.real if m == 0 else np.sqrt(2.0) * (Y.real if m > 0 else Y.imag))
+    want = np.stack(cols, axis=1)
+    got = so.sh_basis(3, torch.tensor(d, dtype=torch.float64)).numpy()
+    assert np.abs(got - want).max() < 1e-13
