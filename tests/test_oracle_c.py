@@ -17,7 +17,8 @@ def _c_render(cam, params, bg):
     return c_port.render_fwd_bwd(cam16, cam.width, cam.height, p, np.asarray(bg, np.float32), w)
 
 
-@pytest.mark.parametrize("name", ["aniso_n80_40x40_rot", "refinit_n300_64x64_saturating", "aniso_n200_96x64_bigsplats"])
+@pytest.mark.parametrize("name", ["aniso_n80_40x40_rot", "aniso_n120_48x40_orbit", "refinit_n300_64x64_saturating",
+                                  "aniso_n200_96x64_bigsplats"])
 def test_c_port_matches_literal_reference_fixture(name):
     if not util.golden_available(name):
         pytest.skip("fixture not generated")
@@ -59,3 +60,29 @@ def test_c_port_matches_torch_oracle_midsize():
                    ("opacity", g["opacity"].reshape(-1, 1)), ("features_dc", g["feat0"].reshape(-1, 1, 3)),
                    ("means2D", res["g_raster"]["means2D"])]:
         assert util.rel_err(torch.tensor(got), o_grads[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("tag", ["c0", "orbit5of16"])
+def test_c_port_stage_fixture_integer_outputs_1080p(tag):
+    """The checker of the full-size GPU tests, itself checked at scale: stages 1-3 of the literal reference at 1080p
+    on 200k anisotropic splats -- pixel centres and depths bit-equal, visibility, int(radii), tile rectangles and tile
+    counts exact (rectangles of splats with an empty AABB are undefined and left out)."""
+    name = f"stages_aniso_n200000_1080p_{tag}"
+    if not util.golden_available(name):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(name)
+    s = so.scene_aniso(int(d["n"]), int(d["seed"]))
+    cam = util.golden_camera(d)
+    cam16 = c_port.camera_block(cam.width, cam.height, cam.fovx, cam.fovy, cam.world_view.numpy())
+    pr = c_port.project(cam16, cam.width, cam.height, s["xyz"].numpy(), s["scaling"].numpy(), s["rotation"].numpy(), None,
+                        s["opacity"].numpy(), True, s["features_dc"].numpy().reshape(-1, 3))
+    assert np.array_equal(pr["means2D"].view(np.uint32), d["ref_means2D_bits"])
+    assert np.array_equal(pr["depths"].view(np.uint32), d["ref_depth_bits"])
+    assert np.array_equal(np.packbits(pr["vis"].astype(bool)), d["ref_vis"])
+    assert np.array_equal(pr["radii"].astype(np.int32), d["ref_radii"].astype(np.int32))
+    assert np.abs(pr["radii"] - d["ref_radii"]).max() <= 5e-7 * np.abs(d["ref_radii"]).max()
+    v = pr["vis"].astype(bool)
+    assert np.array_equal(pr["tiles_touched"][v], d["ref_cnt"][v].astype(np.int32))
+    binned = v & (pr["tiles_touched"] > 0)
+    # the port stores (x0, y0, x1, y1), the fixture (x0, x1, y0, y1)
+    assert np.array_equal(pr["rect"][binned][:, [0, 2, 1, 3]], d["ref_rect"][binned].astype(np.int32))
