@@ -2,7 +2,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py [case ...]
+    python tests/golden/make_golden.py [case ...]        # `config0` (13 minutes) only when named
 
 For every case it
   1. builds a seeded synthetic scene (oracle.splat_oracle generators = SURVEY 8d scenes),
@@ -341,6 +341,51 @@ def make_densify_fixture(n=1500, seed=61):
         ref_scaling=m._scaling.data.numpy(), ref_rotation=m._rotation.data.numpy(), ref_opacity=m._opacity.data.numpy())
 
 
+def make_config0_fixture(n=10000, seed=0, W=256, H=256):
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable case (examples/simple_scene.py: 10 k random-init
+    Gaussians, 256x256, one synthetic camera) -- rendered FORWARD by the literal reference (~12 minutes of its Python
+    pixel loop; its autograd backward at this size does not fit memory).  Stored: the three images, the
+    stage outputs that pin the integer work (pixel-centre and depth bits, radii, visibility, depth order)."""
+    GaussianRenderer, RenderSettings, GaussianModel, TrainingConfig = import_reference()
+    s = so.scene_ref_init(n, seed)
+    cam = so.camera_c0(W, H)
+    m = GaussianModel(TrainingConfig())
+    P = torch.nn.Parameter
+    m._xyz, m._features_dc, m._features_rest = P(s["xyz"].clone()), P(s["features_dc"].clone()), P(s["features_rest"].clone())
+    m._scaling, m._rotation, m._opacity = P(s["scaling"].clone()), P(s["rotation"].clone()), P(s["opacity"].clone())
+    bg = (0.0, 0.0, 0.0)
+    settings = RenderSettings(image_height=H, image_width=W, bg_color=torch.tensor(bg, dtype=torch.float32))
+    rd = GaussianRenderer()
+    t0 = time.time()
+    with torch.no_grad():
+        out = rd.render(RefCamera(cam), RefGaussians(m), settings)
+        t_fwd = time.time() - t0
+        proj = rd._project_gaussians_3d_to_2d(RefCamera(cam), RefGaussians(m))
+        vis = rd._frustum_culling(proj["means2D"], proj["depths"], proj["radii"], settings)
+        sorted_idx = rd._sort_gaussians_by_depth(vis, proj["depths"])
+        d = proj["depths"][vis]
+        n_ties = int(d.numel() - torch.unique(d).numel())
+        o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
+                                  torch.tensor(bg), H, W, return_stats=True)
+    print(f"[config0] literal reference forward {t_fwd:.1f}s  visible {int(vis.sum())}/{n}  visible depth ties {n_ties}"
+          f"  saturated px {int((out['alpha'] >= 0.995).sum())}")
+    print("   oracle vs literal:  image %.2e  alpha %.2e  depth %.2e  means2D bit-equal %.4f  depths bit-equal %.4f"
+          "  int(radii) mismatches %d  vis mismatches %d" % (
+              float((o["image"] - out["image"]).abs().max()), float((o["alpha"] - out["alpha"]).abs().max()),
+              float((o["depth"] - out["depth"]).abs().max()),
+              float((o["viewspace_points"].view(torch.int32) == proj["means2D"].view(torch.int32)).float().mean()),
+              float((o["depths"].view(torch.int32) == proj["depths"].view(torch.int32)).float().mean()),
+              int((o["radii"].int() != proj["radii"].int()).sum()), int((o["visibility_filter"] != vis).sum())))
+    np.savez_compressed(
+        os.path.join(HERE, f"config0_refinit_n{n}_{W}x{H}_c0.npz"),
+        n=np.array(n), seed=np.array(seed), cam_WV=cam.world_view.numpy(), cam_fov=np.array([cam.fovx, cam.fovy]),
+        size_WH=np.array([W, H]), bg=np.array(bg, dtype=np.float32), n_depth_ties=np.array(n_ties),
+        ref_image=out["image"].numpy(), ref_alpha=out["alpha"].numpy(), ref_depth=out["depth"].numpy(),
+        ref_means2D=out["viewspace_points"].numpy(), ref_depths=proj["depths"].numpy(), ref_radii=out["radii"].numpy(),
+        ref_conics=out["conics"].numpy(), ref_vis=out["visibility_filter"].numpy(), ref_sorted_idx=sorted_idx.numpy(),
+        ref_seconds=np.array(t_fwd))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     want = sys.argv[1:] or (["kat", "stages", "densify"] + list(CASES))
@@ -351,5 +396,7 @@ if __name__ == "__main__":
             make_stage_fixture()
         elif c == "densify":
             make_densify_fixture()
+        elif c == "config0":
+            make_config0_fixture()
         else:
             make_case(c)

@@ -86,3 +86,23 @@ def test_c_port_stage_fixture_integer_outputs_1080p(tag):
     binned = v & (pr["tiles_touched"] > 0)
     # the port stores (x0, y0, x1, y1), the fixture (x0, x1, y0, y1)
     assert np.array_equal(pr["rect"][binned][:, [0, 2, 1, 3]], d["ref_rect"][binned].astype(np.int32))
+
+
+def test_c_port_matches_the_literal_reference_on_config0():
+    """BASELINE configs[0] through the C port against the literal reference's recorded forward frame."""
+    if not util.golden_available(util.CONFIG0):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(util.CONFIG0)
+    s = so.scene_ref_init(int(d["n"]), int(d["seed"]))
+    cam = util.golden_camera(d)
+    cam16 = c_port.camera_block(cam.width, cam.height, cam.fovx, cam.fovy, cam.world_view.numpy())
+    p = {k: s[k].numpy() for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
+    res = c_port.render_fwd_bwd(cam16, cam.width, cam.height, p, d["bg"], None, backward=False)
+    pr = res["proj"]
+    assert np.array_equal(pr["means2D"].view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert np.array_equal(pr["depths"].view(np.uint32), d["ref_depths"].view(np.uint32))
+    assert np.array_equal(pr["vis"].astype(bool), d["ref_vis"])
+    assert np.array_equal(pr["radii"].astype(np.int64), d["ref_radii"].astype(np.int64))
+    util.assert_depth_order_equal_up_to_ties(res["sorted_ids"], d["ref_sorted_idx"], d["ref_depths"])
+    for k in ("image", "alpha", "depth"):
+        assert np.abs(res[k] - d["ref_" + k]).max() < 1e-5, k

@@ -173,3 +173,28 @@ def test_sh_basis_of_the_oracle_equals_scipy_spherical_harmonics():
     want = np.stack(cols, axis=1)
     got = so.sh_basis(3, torch.tensor(d, dtype=torch.float64)).numpy()
     assert np.abs(got - want).max() < 1e-13
+
+
+def test_oracle_matches_the_literal_reference_on_config0():
+    """BASELINE configs[0] (10 k random-init Gaussians, 256x256, C0): the literal reference's forward frame
+    (~12 minutes of its pixel loop, recorded by make_golden.py config0) against the oracle."""
+    import numpy as np
+    import torch
+    from oracle import splat_oracle as so
+    if not util.golden_available(util.CONFIG0):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(util.CONFIG0)
+    s = so.scene_ref_init(int(d["n"]), int(d["seed"]))
+    cam = util.golden_camera(d)
+    with torch.no_grad():
+        o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
+                                  torch.tensor(d["bg"]), cam.height, cam.width, return_stats=True)
+    assert np.array_equal(o["viewspace_points"].numpy().view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert np.array_equal(o["depths"].numpy().view(np.uint32), d["ref_depths"].view(np.uint32))
+    assert np.array_equal(o["visibility_filter"].numpy(), d["ref_vis"])
+    assert np.array_equal(o["radii"].numpy().astype(np.int64), d["ref_radii"].astype(np.int64))
+    vis = torch.tensor(d["ref_vis"])
+    util.assert_depth_order_equal_up_to_ties(so.sort_by_depth(vis, o["depths"]).numpy(), d["ref_sorted_idx"], d["ref_depths"])
+    assert util.rel_err(o["conics"], torch.tensor(d["ref_conics"])) < 1e-5
+    for k in ("image", "alpha", "depth"):
+        assert util.max_abs(o[k], torch.tensor(d["ref_" + k])) < 1e-5, k
