@@ -341,19 +341,17 @@ def make_densify_fixture(n=1500, seed=61):
         ref_scaling=m._scaling.data.numpy(), ref_rotation=m._rotation.data.numpy(), ref_opacity=m._opacity.data.numpy())
 
 
-def make_config0_fixture(n=10000, seed=0, W=256, H=256):
-    """BASELINE.json configs[0] -- the reference's own CPU-runnable case (examples/simple_scene.py: 10 k random-init
-    Gaussians, 256x256, one synthetic camera) -- rendered FORWARD by the literal reference (~12 minutes of its Python
-    pixel loop; its autograd backward at this size does not fit memory).  Stored: the three images, the
-    stage outputs that pin the integer work (pixel-centre and depth bits, radii, visibility, depth order)."""
+def _forward_fixture(name, s, cam, bg, extra):
+    """Forward frame of the literal reference (no autograd: its backward does not fit memory beyond a few hundred
+    splats) + the stage outputs that pin the integer work: pixel-centre and depth bits, radii, visibility,
+    depth order."""
     GaussianRenderer, RenderSettings, GaussianModel, TrainingConfig = import_reference()
-    s = so.scene_ref_init(n, seed)
-    cam = so.camera_c0(W, H)
+    W, H = cam.width, cam.height
+    n = s["xyz"].shape[0]
     m = GaussianModel(TrainingConfig())
     P = torch.nn.Parameter
     m._xyz, m._features_dc, m._features_rest = P(s["xyz"].clone()), P(s["features_dc"].clone()), P(s["features_rest"].clone())
     m._scaling, m._rotation, m._opacity = P(s["scaling"].clone()), P(s["rotation"].clone()), P(s["opacity"].clone())
-    bg = (0.0, 0.0, 0.0)
     settings = RenderSettings(image_height=H, image_width=W, bg_color=torch.tensor(bg, dtype=torch.float32))
     rd = GaussianRenderer()
     t0 = time.time()
@@ -367,8 +365,8 @@ def make_config0_fixture(n=10000, seed=0, W=256, H=256):
         n_ties = int(d.numel() - torch.unique(d).numel())
         o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
                                   torch.tensor(bg), H, W, return_stats=True)
-    print(f"[config0] literal reference forward {t_fwd:.1f}s  visible {int(vis.sum())}/{n}  visible depth ties {n_ties}"
-          f"  saturated px {int((out['alpha'] >= 0.995).sum())}")
+    print(f"[{name}] literal reference forward {t_fwd:.1f}s  visible {int(vis.sum())}/{n}  visible depth ties {n_ties}"
+          f"  saturated px {int((out['alpha'] >= 0.995).sum())}  clamped ch {int((out['image'] >= 1).sum())}")
     print("   oracle vs literal:  image %.2e  alpha %.2e  depth %.2e  means2D bit-equal %.4f  depths bit-equal %.4f"
           "  int(radii) mismatches %d  vis mismatches %d" % (
               float((o["image"] - out["image"]).abs().max()), float((o["alpha"] - out["alpha"]).abs().max()),
@@ -377,13 +375,42 @@ def make_config0_fixture(n=10000, seed=0, W=256, H=256):
               float((o["depths"].view(torch.int32) == proj["depths"].view(torch.int32)).float().mean()),
               int((o["radii"].int() != proj["radii"].int()).sum()), int((o["visibility_filter"] != vis).sum())))
     np.savez_compressed(
-        os.path.join(HERE, f"config0_refinit_n{n}_{W}x{H}_c0.npz"),
-        n=np.array(n), seed=np.array(seed), cam_WV=cam.world_view.numpy(), cam_fov=np.array([cam.fovx, cam.fovy]),
+        os.path.join(HERE, name + ".npz"),
+        n=np.array(n), cam_WV=cam.world_view.numpy(), cam_fov=np.array([cam.fovx, cam.fovy]),
         size_WH=np.array([W, H]), bg=np.array(bg, dtype=np.float32), n_depth_ties=np.array(n_ties),
         ref_image=out["image"].numpy(), ref_alpha=out["alpha"].numpy(), ref_depth=out["depth"].numpy(),
         ref_means2D=out["viewspace_points"].numpy(), ref_depths=proj["depths"].numpy(), ref_radii=out["radii"].numpy(),
         ref_conics=out["conics"].numpy(), ref_vis=out["visibility_filter"].numpy(), ref_sorted_idx=sorted_idx.numpy(),
-        ref_seconds=np.array(t_fwd))
+        ref_seconds=np.array(t_fwd), **extra)
+
+
+def make_config0_fixture(n=10000, seed=0, W=256, H=256):
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable case (examples/simple_scene.py: 10 k random-init
+    Gaussians, 256x256, one synthetic camera) -- rendered FORWARD by the literal reference (~13 minutes of its Python
+    pixel loop)."""
+    _forward_fixture(f"config0_refinit_n{n}_{W}x{H}_c0", so.scene_ref_init(n, seed), so.camera_c0(W, H), (0.0, 0.0, 0.0),
+                     dict(seed=np.array(seed)))
+
+
+SATURATING = dict(n=3000, seed=23, W=192, H=128, cam=(3, 11), bg=(0.2, 0.3, 0.1), scale_boost=math.log(4.0), opacity_boost=2.0)
+
+
+def saturating_scene(spec=SATURATING):
+    s = so.scene_aniso(spec["n"], spec["seed"])
+    s["scaling"] = s["scaling"] + spec["scale_boost"]
+    s["opacity"] = s["opacity"] + spec["opacity_boost"]
+    return s, so.camera_orbit(spec["cam"][0], spec["cam"][1], spec["W"], spec["H"])
+
+
+def make_saturating_fixture():
+    """The termination rule at scale against the literal reference: 3 000 anisotropic, enlarged, mostly opaque splats
+    seen from an orbit camera at 192x128 over a non-zero background -- two thirds of the pixels reach A >= 0.995 and
+    stop early (renderer.py:352), hundreds of channels clamp (renderer.py:359), lists of ~340 entries per tile."""
+    s, cam = saturating_scene()
+    sp = SATURATING
+    _forward_fixture(f"aniso_n{sp['n']}_{sp['W']}x{sp['H']}_orbit_saturating_fwd", s, cam, sp["bg"],
+                     dict(seed=np.array(sp["seed"]), scale_boost=np.array(sp["scale_boost"]), opacity_boost=np.array(sp["opacity_boost"]),
+                          orbit=np.array(sp["cam"])))
 
 
 if __name__ == "__main__":
@@ -398,5 +425,7 @@ if __name__ == "__main__":
             make_densify_fixture()
         elif c == "config0":
             make_config0_fixture()
+        elif c == "saturating":
+            make_saturating_fixture()
         else:
             make_case(c)

@@ -106,3 +106,27 @@ def test_c_port_matches_the_literal_reference_on_config0():
     util.assert_depth_order_equal_up_to_ties(res["sorted_ids"], d["ref_sorted_idx"], d["ref_depths"])
     for k in ("image", "alpha", "depth"):
         assert np.abs(res[k] - d["ref_" + k]).max() < 1e-5, k
+
+
+def test_c_port_matches_the_literal_reference_on_the_saturating_midsize_frame():
+    """The C port (its own expf) against the literal reference where two thirds of the pixels terminate early: pixels
+    may stop one entry apart, counted and bounded; all others within 1e-5."""
+    if not util.golden_available(util.SATURATING):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(util.SATURATING)
+    s = util.saturating_scene(d)
+    cam = util.golden_camera(d)
+    cam16 = c_port.camera_block(cam.width, cam.height, cam.fovx, cam.fovy, cam.world_view.numpy())
+    p = {k: s[k].numpy() for k in ("xyz", "scaling", "rotation", "opacity", "features_dc")}
+    res = c_port.render_fwd_bwd(cam16, cam.width, cam.height, p, d["bg"], None, backward=False)
+    pr = res["proj"]
+    assert np.array_equal(pr["means2D"].view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert np.array_equal(pr["depths"].view(np.uint32), d["ref_depths"].view(np.uint32))
+    assert np.array_equal(pr["vis"].astype(bool), d["ref_vis"])
+    assert np.array_equal(pr["radii"].astype(np.int64), d["ref_radii"].astype(np.int64))
+    with torch.no_grad():        # the oracle's per-pixel walk lengths stand for the literal reference's (test_oracle_golden)
+        o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
+                                  torch.tensor(d["bg"]), cam.height, cam.width, return_stats=True)
+    got = {k: torch.tensor(res[k]) for k in ("image", "alpha", "depth")}
+    ref = {k: torch.tensor(d["ref_" + k]) for k in ("image", "alpha", "depth")}
+    util.assert_images_close(got, ref, torch.tensor(res["n_consumed"]), o["n_consumed"], "C port, saturating frame")

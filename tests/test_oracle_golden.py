@@ -198,3 +198,29 @@ def test_oracle_matches_the_literal_reference_on_config0():
     assert util.rel_err(o["conics"], torch.tensor(d["ref_conics"])) < 1e-5
     for k in ("image", "alpha", "depth"):
         assert util.max_abs(o[k], torch.tensor(d["ref_" + k])) < 1e-5, k
+
+
+def test_oracle_matches_the_literal_reference_on_the_saturating_midsize_frame():
+    """3 000 enlarged, mostly opaque anisotropic splats at 192x128: two thirds of the pixels stop at A >= 0.995
+    (renderer.py:352).  The oracle follows the reference's fp32 operation order with the same libm, so not a single
+    pixel may stop at a different entry: every pixel within 1e-5."""
+    import numpy as np
+    import torch
+    from oracle import splat_oracle as so
+    if not util.golden_available(util.SATURATING):
+        pytest.skip("fixture not generated")
+    d = util.load_golden(util.SATURATING)
+    s = util.saturating_scene(d)
+    cam = util.golden_camera(d)
+    with torch.no_grad():
+        o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
+                                  torch.tensor(d["bg"]), cam.height, cam.width, return_stats=True)
+    assert int(d["n_depth_ties"]) == 0
+    assert np.array_equal(o["viewspace_points"].numpy().view(np.uint32), d["ref_means2D"].view(np.uint32))
+    assert np.array_equal(o["depths"].numpy().view(np.uint32), d["ref_depths"].view(np.uint32))
+    assert np.array_equal(o["visibility_filter"].numpy(), d["ref_vis"])
+    assert np.array_equal(o["radii"].numpy().astype(np.int64), d["ref_radii"].astype(np.int64))
+    assert np.array_equal(so.sort_by_depth(torch.tensor(d["ref_vis"]), o["depths"]).numpy(), d["ref_sorted_idx"])
+    assert int((torch.tensor(d["ref_alpha"]) >= 0.995).sum()) > 10000          # the case is what it claims to be
+    for k in ("image", "alpha", "depth"):
+        assert util.max_abs(o[k], torch.tensor(d["ref_" + k])) < 1e-5, k

@@ -1,9 +1,10 @@
-"""BASELINE configs[0] on the GPU against the LITERAL reference: 10 000 random-init Gaussians (create_from_random, CPU
+"""Two frames of the LITERAL reference too large for its autograd, on the GPU.  (1) BASELINE configs[0]: 10 000 random-init Gaussians (create_from_random, CPU
 seed 0), 256x256, camera C0 -- the reference's own CPU-runnable case (examples/simple_scene.py).  The fixture
 (tests/golden/make_golden.py config0) holds the forward frame GaussianRenderer.render of /root/reference produced in
 ~12 minutes of its Python pixel loop (src/core/renderer.py:31-114); its autograd backward does not fit memory at this
 size, so the gradients of the same frame are compared with the C port, which tests/test_oracle_c.py pins to
-this very fixture.
+this very fixture.  (2) A 192x128 frame of 3 000 enlarged, mostly opaque splats in which two thirds of the pixels terminate
+early (make_golden.py saturating, 359 s).  This file sorts last on purpose: it is the newest evidence, the older suites run first.
 
 Tolerances: BASELINE.json's -- visibility, integer radii, pixel centres (bits), depth order exact; image / alpha / depth
 <= 1e-4 absolute; gradients <= 1e-3 * max|g_ref|.  The reference's depth sort is unstable (renderer.py:235), so ids are
@@ -93,3 +94,56 @@ def test_config0_frame_matches_the_literal_reference_and_gradients_match_the_c_p
         assert util.rel_err(grads[k], torch.tensor(want)) < GRAD_TOL, k
     assert float(grads["rotation"].abs().max()) <= 1e-5 * float(grads["xyz"].abs().max())
     assert grads["features_rest"] is not None and float(grads["features_rest"].abs().max()) == 0.0
+
+
+def test_saturating_midsize_frame_matches_the_literal_reference_where_two_thirds_of_the_pixels_terminate():
+    """3 000 enlarged, mostly opaque anisotropic splats, orbit camera, 192x128, non-zero background: 16 090 of 24 576
+    pixels reach A >= 0.995 and stop early (renderer.py:352), 644 channels clamp (renderer.py:359).  The fixture is
+    the literal reference's forward frame (make_golden.py `saturating`, 359 s).  A pixel whose accumulated opacity
+    crosses 0.995 one entry earlier or later than the reference's (MUFU ex2 vs libm exp) is counted, bounded and
+    excluded; the oracle -- bit-equal to the literal reference in alpha and depth on this frame
+    (tests/test_oracle_golden.py) -- supplies the reference's per-pixel walk lengths.  Then the whole-frame comparison
+    of tests/test_gpu_fullsize.py (every stage, every parameter gradient, against the C port) on the same scene."""
+    if not util.golden_available(util.SATURATING):
+        pytest.skip("fixture not generated")
+    from tests.test_gpu_fullsize import _whole_frame
+    d = util.load_golden(util.SATURATING)
+    s = util.saturating_scene(d)
+    cam = util.golden_camera(d)
+    W, H = cam.width, cam.height
+    bg = tuple(float(v) for v in d["bg"])
+    model = util.cuda_model_from_params(s)
+    rd, out, _, _ = _whole_frame(model, util.cuda_camera(cam), W, H, "saturating 192x128", bg=bg)
+
+    vis = d["ref_vis"].astype(bool)
+    assert np.array_equal(out["visibility_filter"].cpu().numpy(), vis)
+    m2 = out["viewspace_points"].detach().cpu().numpy()
+    assert np.array_equal(m2.view(np.uint32)[vis], d["ref_means2D"].view(np.uint32)[vis])
+    radii = out["radii"].detach().cpu().numpy()
+    boundary = _boundary_radii(radii, d["ref_radii"], vis)
+    binned = rd._last_debug["tiles_touched"].cpu().numpy() > 0
+    ref_order = d["ref_sorted_idx"][binned[d["ref_sorted_idx"]]]
+    assert np.array_equal(rd._last_debug["sorted_ids"].cpu().numpy(), ref_order), "depth order (no ties in this scene)"
+
+    with torch.no_grad():
+        o = so.render_from_params(cam, s["xyz"], s["scaling"], s["rotation"], s["opacity"], s["features_dc"],
+                                  torch.tensor(d["bg"]), H, W, return_stats=True)
+    ncg = rd._last_debug["n_consumed"].cpu().numpy().astype(np.int64)
+    ncw = o["n_consumed"].numpy().astype(np.int64)
+    same = ncg == ncw
+    flips = int((~same).sum())
+    assert flips <= 2e-3 * same.size, f"{flips} termination flips of {same.size} pixels"
+    if flips:
+        assert int(np.abs(ncg - ncw).max()) <= 32
+    worst = {}
+    for k in ("image", "alpha", "depth"):
+        diff = np.abs(out[k].detach().cpu().numpy().astype(np.float64) - d["ref_" + k].astype(np.float64))
+        m = np.broadcast_to(same[None], diff.shape)
+        worst[k] = float(diff[m].max())
+        if flips:
+            scale = 1.0 if k != "depth" else float(np.abs(d["ref_depth"]).max()) + 1.0
+            assert float(diff[~m].max()) < 1e-2 * scale, f"{k} on a flipped pixel"
+    print(f"saturating frame vs literal reference: {worst}; termination flips {flips} of {same.size}; boundary radii {boundary.tolist()}")
+    if boundary.size == 0:
+        for k, v in worst.items():
+            assert v < IMG_TOL, f"{k} differs from the literal reference by {v:.3e}"

@@ -151,3 +151,14 @@ def assert_depth_order_equal_up_to_ties(got_ids, ref_ids, depths) -> int:
     assert np.array_equal(got_ids[~tied], ref_ids[~tied]), "depth order differs outside tie groups"
     assert np.array_equal(np.sort(got_ids[tied]), np.sort(ref_ids[tied]))
     return int(tied.sum())
+
+
+SATURATING = "aniso_n3000_192x128_orbit_saturating_fwd"   # literal reference forward, 2/3 of the pixels terminate early
+
+
+def saturating_scene(d):
+    """The scene make_golden.py `saturating` rendered, rebuilt from the parameters stored in the fixture."""
+    s = so.scene_aniso(int(d["n"]), int(d["seed"]))
+    s["scaling"] = s["scaling"] + float(d["scale_boost"])
+    s["opacity"] = s["opacity"] + float(d["opacity_boost"])
+    return s
