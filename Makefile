@@ -23,7 +23,7 @@ $(BUILDDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/gsplat_b200.h
 
 $(LIBDIR)/libgsplat_b200.so: $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared -o $@ $(CU_OBJS) -cudart static
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJS) -cudart static
 
 oracle: oracle/_ref/liboracle.so
 
@@ -40,4 +40,4 @@ clean:
 variant:
 	@mkdir -p build/variants/$(NAME)
 	for f in abi project binsort depthsort raster peer densify loss; do $(NVCC) $(NVCCFLAGS) $(DEFS) -c $(CSRC)/$$f.cu -o build/variants/$(NAME)/$$f.o || exit 1; done
-	$(NVCC) -shared -o build/variants/libgsplat_b200_$(NAME).so build/variants/$(NAME)/*.o -cudart static
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/libgsplat_b200_$(NAME).so build/variants/$(NAME)/*.o -cudart static
