@@ -97,6 +97,10 @@ CASES = {
                                 bg=(0.25, 0.1, 0.4), scale_boost=math.log(10.0), opacity_boost=1.0),
     "aniso_n200_96x64_bigsplats": dict(scene="aniso", n=200, seed=11, W=96, H=64, cam=("c0",),
                                        bg=(0.6, 0.6, 0.6), scale_boost=math.log(25.0), opacity_boost=-1.0),
+    # the largest frame the reference's autograd finishes here: 1.2 M pixel x entry evaluations, ~5 GB of graph; no pixel
+    # saturates (max alpha 0.98), so no termination flip can blur the gradient comparison
+    "aniso_n1000_128x96_orbit": dict(scene="aniso", n=1000, seed=37, W=128, H=96, cam=("orbit", 2, 7),
+                                     bg=(0.1, 0.2, 0.3), scale_boost=math.log(3.0), opacity_boost=-0.4),
     # other tile sizes (renderer.py:24 takes any): which splats a pixel sees depends on its tile's list (3-sigma rectangles
     # against tiles, renderer.py:263-298), so the image itself changes with the tile size
     "aniso_n100_48x40_tile8": dict(scene="aniso", n=100, seed=13, W=48, H=40, cam=("orbit", 2, 9), tile=8,
