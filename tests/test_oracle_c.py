@@ -18,7 +18,7 @@ def _c_render(cam, params, bg):
 
 
 @pytest.mark.parametrize("name", ["aniso_n80_40x40_rot", "aniso_n120_48x40_orbit", "refinit_n300_64x64_saturating",
-                                  "aniso_n200_96x64_bigsplats"])
+                                  "aniso_n200_96x64_bigsplats", "aniso_n1000_128x96_orbit"])
 def test_c_port_matches_literal_reference_fixture(name):
     if not util.golden_available(name):
         pytest.skip("fixture not generated")

@@ -11,7 +11,7 @@ from oracle import splat_oracle as so
 from tests import util
 
 
-@pytest.mark.parametrize("name", util.RENDER_CASES)
+@pytest.mark.parametrize("name", util.RENDER_CASES + [util.RENDER_CASE_LARGE])
 def test_oracle_matches_literal_reference_forward_and_grads(name):
     if not util.golden_available(name):
         pytest.skip("fixture not generated")

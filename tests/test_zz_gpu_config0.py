@@ -147,3 +147,12 @@ def test_saturating_midsize_frame_matches_the_literal_reference_where_two_thirds
     if boundary.size == 0:
         for k, v in worst.items():
             assert v < IMG_TOL, f"{k} differs from the literal reference by {v:.3e}"
+
+
+def test_largest_literal_reference_gradient_fixture():
+    """1 000 anisotropic splats at 128x96 from an orbit camera: the largest frame whose autograd backward the literal
+    reference finishes (289 s forward, 310 s backward, 25 GB of graph).  Same checks as the small fixtures of
+    tests/test_gpu_parity.py: integer outputs exact, per-tile lists entry for entry, image / alpha / depth <= 1e-4, every
+    parameter gradient and viewspace_points.grad <= 1e-3 * max|g_ref| against the reference's own autograd."""
+    from tests.test_gpu_parity import test_golden_render_forward_and_gradients as golden_case
+    golden_case(util.RENDER_CASE_LARGE)

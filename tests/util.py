@@ -13,6 +13,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PARAM_KEYS = ("xyz", "scaling", "rotation", "opacity", "features_dc")
 RENDER_CASES = ["aniso_n80_40x40_rot", "aniso_n120_48x40_orbit", "refinit_n300_64x64_saturating",
                 "aniso_n200_96x64_bigsplats", "aniso_n100_48x40_tile8", "aniso_n90_50x44_tile12", "aniso_n100_72x56_tile32"]
+# the largest frame the literal reference's autograd finishes (1 000 splats, 128x96: 289 s forward, 310 s backward, 25 GB);
+# same layout as RENDER_CASES, checked on the GPU by tests/test_zz_gpu_config0.py
+RENDER_CASE_LARGE = "aniso_n1000_128x96_orbit"
 
 
 def golden_tile_size(d) -> int:
