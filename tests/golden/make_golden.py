@@ -2,7 +2,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py [case ...]        # `config0` (13 minutes) only when named
+    python tests/golden/make_golden.py [case ...]        # config0 / saturating / aniso_n1000_128x96_orbit only when named
 
 For every case it
   1. builds a seeded synthetic scene (oracle.splat_oracle generators = SURVEY 8d scenes),
@@ -419,7 +419,8 @@ def make_saturating_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    want = sys.argv[1:] or (["kat", "stages", "densify"] + list(CASES))
+    # named only: config0 (13 min), saturating (6 min), aniso_n1000_128x96_orbit (10 min, 25 GB of autograd graph)
+    want = sys.argv[1:] or (["kat", "stages", "densify"] + [c for c in CASES if c != "aniso_n1000_128x96_orbit"])
     for c in want:
         if c == "kat":
             make_kat_two_splats()
