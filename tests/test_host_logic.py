@@ -112,3 +112,26 @@ def test_fused_loss_object_behaves_like_a_scalar_loss_for_the_step_drivers():
     FusedLoss(torch.tensor(0.0), [torch.zeros(3)], [torch.ones(3)]).backward()
     with __import__("pytest").raises(RuntimeError):
         import_module("mini-3d-gaussian-splatting_b200.losses").l1_loss(torch.zeros(3), torch.zeros(3))     # CPU tensors: no fallback
+
+
+def test_camera_block_of_the_renderer_equals_the_oracles_camera():
+    """The 20 host floats gs_project_fwd receives (renderer._camera_block): W2C rotation and translation, intrinsics
+    rounded once to fp32 as renderer.py:140-152 does, and the camera centre -R^T t -- against the oracle's camera (pinned
+    to the literal reference by the stage fixtures) and the C port's block, for every camera the tests and bench use."""
+    import numpy as np
+    from importlib import import_module
+    from oracle import c_port, splat_oracle as so
+    rmod = import_module("mini-3d-gaussian-splatting_b200.renderer")
+    cams = [so.camera_c0(1920, 1080), so.camera_c0(256, 256), so.camera_orbit(5, 16, 1920, 1080), so.camera_orbit(1, 8, 1600, 1200),
+            so.camera_orbit(3, 7, 50, 44)]
+    for cam in cams:
+        block = np.array(list(rmod._camera_block(gb.Camera(cam.width, cam.height, cam.fovx, cam.fovy, world_view=cam.world_view))),
+                         dtype=np.float32)
+        c16 = c_port.camera_block(cam.width, cam.height, cam.fovx, cam.fovy, cam.world_view.numpy())
+        assert np.array_equal(block[:16].view(np.uint32), c16.view(np.uint32))
+        fx, fy, cx, cy = (float(v) for v in cam.intrinsics())
+        assert [float(v) for v in block[12:16]] == [fx, fy, cx, cy]
+        wv = cam.world_view.double()
+        centre = -(wv[:3, :3].T @ wv[:3, 3])
+        assert np.allclose(block[16:19], centre.numpy(), rtol=0, atol=1e-6)
+        assert block[19] == 0.0
