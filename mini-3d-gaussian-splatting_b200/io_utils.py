@@ -44,6 +44,24 @@ class CameraUtils:
         return view
 
     @staticmethod
+    def build_projection_matrix(znear: float, zfar: float, fovX: float, fovY: float,
+                                width: Optional[int] = None, height: Optional[int] = None) -> torch.Tensor:
+        """OpenGL-style perspective matrix of camera.py:143-188 (the reference defines it twice under one name -- once from
+        the half-angle tangents, once from focal lengths and the image size -- and both give the same matrix, so `width` /
+        `height` are accepted and not needed).  The renderer never reads it (renderer.py:140-152 takes fx, fy from the
+        fields of view); it is here for callers that project points themselves."""
+        import math
+        tx = max(abs(math.tan(fovX * 0.5)), 1e-6)
+        ty = max(abs(math.tan(fovY * 0.5)), 1e-6)
+        P = torch.zeros(4, 4, dtype=torch.float32)
+        P[0, 0] = 1.0 / tx
+        P[1, 1] = 1.0 / ty
+        P[2, 2] = -(zfar + znear) / (zfar - znear)
+        P[2, 3] = -(2.0 * zfar * znear) / (zfar - znear)
+        P[3, 2] = -1.0
+        return P
+
+    @staticmethod
     def focal_to_fov(focal: float, pixels: int) -> float:
         return 2.0 * float(np.arctan(pixels / (2.0 * focal)))
 

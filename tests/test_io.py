@@ -42,6 +42,38 @@ def test_world_view_matrix_matches_reference_function():
     assert CameraUtils.focal_to_fov(f, 64) == pytest.approx(math.radians(60))
 
 
+def test_projection_matrix_is_the_references_in_both_of_its_forms():
+    """tests/test_camera.py of the reference wants its two definitions (half-angle tangents; focal lengths and image
+    size) to agree; only the second survives in its class (same method name twice), so that one is called live when the
+    reference tree is present, and the first is restated here."""
+    cases = [(60, 45, 0.1, 1000.0, 640, 480), (90, 67.5, 0.1, 500.0, 1920, 1080), (30, 22.5, 0.5, 2000.0, 800, 600)]
+    ref = None
+    try:
+        sys.path.insert(0, "/root/reference")
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            from src.core.camera import CameraUtils as RefCU
+        ref = RefCU.build_projection_matrix
+    except ImportError:
+        pass
+    finally:
+        if "/root/reference" in sys.path:
+            sys.path.remove("/root/reference")
+    for fx_deg, fy_deg, zn, zf, w, h in cases:
+        fx, fy = math.radians(fx_deg), math.radians(fy_deg)
+        P = CameraUtils.build_projection_matrix(zn, zf, fx, fy)
+        assert torch.equal(P, CameraUtils.build_projection_matrix(zn, zf, fx, fy, w, h))
+        tangents = torch.tensor([[1 / math.tan(fx / 2), 0, 0, 0], [0, 1 / math.tan(fy / 2), 0, 0],
+                                 [0, 0, -(zf + zn) / (zf - zn), -2 * zf * zn / (zf - zn)], [0, 0, -1, 0]], dtype=torch.float32)
+        assert torch.allclose(P, tangents, rtol=1e-6, atol=0)
+        if ref is not None:
+            assert torch.allclose(P, ref(zn, zf, fx, fy, w, h), rtol=1e-6, atol=0)
+        # -z forward: the near and far planes land on NDC z = -1 and +1
+        for z, want in ((-zn, -1.0), (-zf, 1.0)):
+            clip = P @ torch.tensor([0.0, 0.0, z, 1.0])
+            assert float(clip[2] / clip[3]) == pytest.approx(want, abs=1e-4)
+
+
 @pytest.mark.parametrize("ext", [".npz", ".npy", ".ply", ".xyz"])
 def test_point_cloud_round_trip(tmp_path, ext):
     rng = np.random.default_rng(1)
