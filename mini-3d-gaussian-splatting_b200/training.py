@@ -13,16 +13,22 @@ Everything here is host-side torch on device tensors; the kernels are the render
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 
 
 @dataclass
 class TrainingConfig:
-    """Defaults of the reference's dataclass (config/config.py:33-67) that the loop reads."""
+    """The reference's dataclass, field for field (config/config.py:33-67), so `TrainingConfig(**yaml)` of a reference
+    config file constructs; `learning_rate` and `batch_size` are read by nothing there either."""
+    data_path: str = "data/scene"
+    output_path: str = "output"
     iterations: int = 30000
+    learning_rate: float = 0.0025
+    batch_size: int = 1
     position_lr_init: float = 0.00016
     position_lr_final: float = 0.0000016
     position_lr_delay_mult: float = 0.01
@@ -242,3 +248,158 @@ def densification_stress(model, renderer, cameras, settings, controller: Density
         if stats["split"] + stats["cloned"] == 0:
             break
     return {"points": model.get_num_points(), "history": history}
+
+
+class GaussianTrainer:
+    """The reference's trainer surface -- `setup / train / train_step / validate / save_checkpoint / load_checkpoint /
+    get_scene_extent` (src/train/trainer.py:12-97) -- with the loop its docstrings describe; in the reference every one
+    of these methods is `pass`.  One iteration = pick a training camera, render it, L1 against the camera's image,
+    backward, Adam step, densification statistics, and density control on its schedule (trainer.py:45-59).
+
+    The reference's dataset classes are out of scope: cameras are passed in, each carrying its ground-truth
+    image [3,H,W] as `camera._image` (what `Camera(..., image=...)` stores).  Any renderer with the reference's
+    `render(camera, gaussians, settings)` contract works; the default is the B200 one."""
+
+    def __init__(self, config: Optional[TrainingConfig] = None, cameras: Optional[Sequence] = None, gaussians=None,
+                 renderer=None, val_cameras: Optional[Sequence] = None, bg_color: Sequence[float] = (0.0, 0.0, 0.0), seed: int = 0):
+        self.config = config or TrainingConfig()
+        self.cameras = list(cameras or [])
+        self.val_cameras = list(val_cameras or [])
+        self.gaussians = gaussians
+        self.renderer = renderer
+        self.optimizer: Optional[GaussianOptimizer] = None
+        self.density_controller: Optional[DensityController] = None
+        self.loss_fn = l1_loss
+        self.bg_color = tuple(float(v) for v in bg_color)
+        self.iteration = 0
+        self.scene_extent = 0.0
+        self.train_losses: List[float] = []
+        self.val_losses: List[float] = []
+        self._order = torch.Generator().manual_seed(seed)          # camera sampling: reproducible, same on every rank
+
+    # ---- trainer.py:31-43 ---------------------------------------------------------------------------
+    def setup(self) -> None:
+        """Model (the one passed in, else from `<data_path>/points3D.*` when present, else `create_from_random`),
+        renderer, optimiser, density controller, scene extent."""
+        from .renderer import GaussianRenderer
+        from .scene import GaussianModel
+        if self.gaussians is None:
+            self.gaussians = GaussianModel(self.config)
+            pcd = next((os.path.join(self.config.data_path, f) for f in ("points3D.ply", "points3D.txt", "points3D.npz")
+                        if os.path.exists(os.path.join(self.config.data_path, f))), None)
+            if pcd is not None:
+                self.gaussians.create_from_pcd(pcd)
+            else:
+                self.gaussians.create_from_random(10000, 1.0)
+        if self.renderer is None:
+            self.renderer = GaussianRenderer()
+        self.optimizer = GaussianOptimizer(self.gaussians, self.config)
+        self.density_controller = DensityController(self.config)
+        self.scene_extent = self.get_scene_extent()
+
+    def get_scene_extent(self) -> float:
+        """Radius of the camera rig, the scale the densification thresholds are relative to (optimizer.py:61-63 compare
+        sigma with 0.01 / 0.03 x this): 1.1 x the largest distance of a camera centre from the centroid of the centres;
+        with fewer than two cameras, half the diagonal of the model's bounding box."""
+        centres = [c.camera_center for c in self.cameras if hasattr(c, "camera_center")]
+        if len(centres) >= 2:
+            C = torch.stack([torch.as_tensor(c, dtype=torch.float32).reshape(3).cpu() for c in centres])
+            return 1.1 * float((C - C.mean(dim=0)).norm(dim=-1).max())
+        if self.gaussians is not None and self.gaussians.get_num_points() > 0:
+            xyz = self.gaussians.get_xyz.detach()
+            return 0.5 * float((xyz.max(dim=0).values - xyz.min(dim=0).values).norm())
+        return 1.0
+
+    # ---- trainer.py:45-65 ---------------------------------------------------------------------------
+    def _settings(self, camera):
+        from .renderer import RenderSettings
+        dev = self.gaussians.get_xyz.device
+        return RenderSettings(int(camera._height), int(camera._width), torch.tensor(self.bg_color, dtype=torch.float32, device=dev))
+
+    def _target(self, camera) -> torch.Tensor:
+        img = getattr(camera, "_image", None)
+        if img is None:
+            raise ValueError("training cameras carry their ground-truth image as camera._image ([3,H,W])")
+        return img.to(self.gaussians.get_xyz.device, torch.float32)
+
+    def train_step(self, camera) -> Dict[str, float]:
+        """One iteration on `camera` (trainer.py:61-65); returns floats, as the reference's signature says (one host
+        read of the loss per step -- `training.train_step` is the variant that leaves the loss on the device)."""
+        self.iteration += 1
+        res = train_step(self.gaussians, self.renderer, camera, self._target(camera), self.optimizer, self._settings(camera),
+                         self.iteration, self.loss_fn)
+        stats: Dict[str, float] = {"iteration": float(self.iteration), "points": float(self.gaussians.get_num_points())}
+        if self.density_controller.should_densify(self.iteration):
+            n = self.gaussians
+            grad = n.xyz_gradient_accum / n.denom.clamp_min(1.0)           # mean |dL/d means2D| over the views that saw the splat
+            d = self.density_controller.densify_and_prune(n, self.optimizer, self.scene_extent,
+                                                          grad=torch.cat([grad[:, :1], torch.zeros_like(grad[:, 1:])], dim=1))
+            stats.update({k: float(d[k]) for k in ("split", "cloned", "pruned")})
+            stats["points"] = float(n.get_num_points())
+        stats["loss"] = float(res["loss"])
+        return stats
+
+    def train(self, iterations: Optional[int] = None, val_every: int = 0, checkpoint_every: int = 0) -> None:
+        """Main loop (trainer.py:45-59): random training camera, step, density control, periodic validation / checkpoint."""
+        if self.optimizer is None:
+            self.setup()
+        if not self.cameras:
+            raise ValueError("no training cameras")
+        total = self.config.iterations if iterations is None else int(iterations)
+        while self.iteration < total:
+            cam = self.cameras[int(torch.randint(len(self.cameras), (1,), generator=self._order))]
+            self.train_losses.append(self.train_step(cam)["loss"])
+            if val_every and self.iteration % val_every == 0:
+                self.val_losses.append(self.validate()["l1"])
+            if checkpoint_every and self.iteration % checkpoint_every == 0:
+                self.save_checkpoint(self.iteration)
+
+    @torch.no_grad()
+    def validate(self) -> Dict[str, float]:
+        """Mean L1 and PSNR over the validation cameras (the training cameras when none were given)."""
+        cams = self.val_cameras or self.cameras
+        l1s, psnrs = [], []
+        for cam in cams:
+            img = self.renderer.render(cam, self.gaussians, self._settings(cam))["image"]
+            tgt = self._target(cam)
+            l1s.append(float((img - tgt).abs().mean()))
+            psnrs.append(float(-10.0 * torch.log10(((img - tgt) ** 2).mean().clamp_min(1e-12))))
+        return {"l1": sum(l1s) / len(l1s), "psnr": sum(psnrs) / len(psnrs), "views": float(len(cams))}
+
+    # ---- trainer.py:73-83 ---------------------------------------------------------------------------
+    def _checkpoint_path(self, iteration: int) -> str:
+        return os.path.join(self.config.output_path, f"checkpoint_{int(iteration):07d}.pt")
+
+    def save_checkpoint(self, iteration: int) -> None:
+        """Parameters, Adam moments and step counts, the densification statistics, the iteration and the camera-sampling
+        state: `load_checkpoint` followed by `train()` continues exactly where this run would have."""
+        os.makedirs(self.config.output_path, exist_ok=True)
+        g = self.gaussians
+        torch.save({
+            "iteration": int(self.iteration), "scene_extent": float(self.scene_extent),
+            "params": {name: getattr(g, name).detach().cpu() for name in
+                       ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity")},
+            "stats": {"xyz_gradient_accum": g.xyz_gradient_accum.cpu(), "denom": g.denom.cpu(), "max_radii2D": g.max_radii2D.cpu()},
+            "optimizer": self.optimizer.optimizer.state_dict(), "order": self._order.get_state(),
+            "train_losses": list(self.train_losses), "val_losses": list(self.val_losses),
+        }, self._checkpoint_path(iteration))
+
+    def load_checkpoint(self, iteration: int) -> None:
+        ck = torch.load(self._checkpoint_path(iteration), map_location="cpu", weights_only=False)
+        if self.gaussians is None:
+            from .scene import GaussianModel
+            self.gaussians = GaussianModel(self.config)
+        p = ck["params"]
+        self.gaussians.create_from_tensors(p["_xyz"], p["_features_dc"], p["_scaling"], p["_rotation"], p["_opacity"], p["_features_rest"])
+        dev = self.gaussians.get_xyz.device
+        for k, v in ck["stats"].items():
+            setattr(self.gaussians, k, v.to(dev))
+        if self.renderer is None:
+            from .renderer import GaussianRenderer
+            self.renderer = GaussianRenderer()
+        self.optimizer = GaussianOptimizer(self.gaussians, self.config)
+        self.optimizer.optimizer.load_state_dict(ck["optimizer"])
+        self.density_controller = DensityController(self.config)
+        self.iteration, self.scene_extent = int(ck["iteration"]), float(ck["scene_extent"])
+        self._order.set_state(ck["order"])
+        self.train_losses, self.val_losses = list(ck["train_losses"]), list(ck["val_losses"])
