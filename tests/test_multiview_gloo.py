@@ -76,7 +76,9 @@ def worker(rank, world, port, q, oracle=False):
     # gradients must have accumulated in place into the flat buffer (no packing step)
     assert m._xyz.grad.data_ptr() == flat_ptr
     assert buf.flat.data_ptr() == flat_ptr
-    q.put((rank, buf.flat.clone(), buf.max_radii.clone(), ids))
+    # by value (numpy), not as torch tensors: a tensor travels as a handle to the sender's shared memory, and the sender
+    # may have exited by the time the parent opens it
+    q.put((rank, buf.flat.numpy().copy(), buf.max_radii.numpy().copy(), ids))
     dist.destroy_process_group()
 
 
@@ -109,6 +111,7 @@ def test_two_rank_reduced_grads_equal_single_rank_sum(oracle):
     for p in procs:
         p.start()
     got = [q.get(timeout=120) for _ in range(2)]
+    got = [(r, torch.from_numpy(f), torch.from_numpy(m), i) for r, f, m, i in got]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
