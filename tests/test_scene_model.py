@@ -42,7 +42,7 @@ def test_initialisation_shapes_and_statistics_buffers():
     assert float(m.get_xyz.detach().abs().max()) <= 1.0
     assert torch.allclose(m.get_scaling, torch.full((n, 3), 0.02), rtol=1e-6)
     assert torch.allclose(m.get_opacity, torch.full((n, 1), 1.0 / (1.0 + math.exp(2.0))), rtol=1e-6)
-    assert float(m._features_rest.abs().max()) == 0.0
+    assert float(m._features_rest.detach().abs().max()) == 0.0
 
 
 def test_activated_accessors():
