@@ -9,6 +9,6 @@ from .scene import Camera, GaussianModel  # noqa: F401
 
 __all__ = ["GaussianRenderer", "RenderSettings", "GaussianModel", "Camera"]
 from . import losses, multiview, training  # noqa: F401,E402
-from .training import (DensityController, GaussianOptimizer, GaussianTrainer, LearningRateScheduler, TrainingConfig,  # noqa: F401,E402
+from .training import (ConfigManager, DensityController, GaussianOptimizer, GaussianTrainer, LearningRateScheduler, TrainingConfig,  # noqa: F401,E402
                        train_step)
 from .io_utils import CameraUtils, IOUtils  # noqa: F401,E402

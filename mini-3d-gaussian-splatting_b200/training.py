@@ -46,6 +46,27 @@ class TrainingConfig:
     device: str = "cuda"
 
 
+class ConfigManager:
+    """config/config.py:69-94: the training configuration as a YAML file."""
+
+    @staticmethod
+    def load_from_yaml(config_path: str) -> TrainingConfig:
+        import yaml
+        with open(config_path, "r", encoding="utf-8") as f:
+            return TrainingConfig(**(yaml.safe_load(f) or {}))
+
+    @staticmethod
+    def save_to_yaml(config: TrainingConfig, config_path: str) -> None:
+        import yaml
+        os.makedirs(os.path.dirname(os.path.abspath(config_path)), exist_ok=True)
+        with open(config_path, "w", encoding="utf-8") as f:
+            yaml.safe_dump({k: getattr(config, k) for k in config.__dataclass_fields__}, f, allow_unicode=True)
+
+    @staticmethod
+    def get_default_config() -> TrainingConfig:
+        return TrainingConfig()
+
+
 class LearningRateScheduler:
     """Cosine decay from lr_init to lr_final over max_steps, scaled during the first
     lr_delay_steps by a ramp from lr_delay_mult to 1 (optimizer.py:7-32)."""

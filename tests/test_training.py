@@ -22,6 +22,27 @@ def test_learning_rate_schedule_matches_reference_formula():
     assert gb.LearningRateScheduler(1.0, 0.5, 0, 1.0, 0).get_lr(5) == 0.5
 
 
+def test_training_config_is_the_references_field_for_field_and_round_trips_through_yaml(tmp_path):
+    import dataclasses
+    cfg = gb.ConfigManager.get_default_config()
+    path = str(tmp_path / "sub" / "config.yaml")
+    changed = dataclasses.replace(cfg, iterations=123, densify_grad_threshold=5e-4, device="cpu", output_path="out/x")
+    gb.ConfigManager.save_to_yaml(changed, path)
+    assert gb.ConfigManager.load_from_yaml(path) == changed
+    try:                                       # the literal reference dataclass, when the reference tree is present
+        import contextlib, io, sys
+        sys.path.insert(0, "/root/reference")
+        with contextlib.redirect_stdout(io.StringIO()):
+            from config.config import TrainingConfig as RefConfig
+        assert dataclasses.asdict(RefConfig()) == dataclasses.asdict(cfg)
+        assert [f.name for f in dataclasses.fields(RefConfig)] == [f.name for f in dataclasses.fields(cfg)]
+    except ImportError:
+        pass
+    finally:
+        if "/root/reference" in sys.path:
+            sys.path.remove("/root/reference")
+
+
 def test_densify_schedule():
     c = gb.DensityController(gb.TrainingConfig())
     assert not c.should_densify(400) and c.should_densify(500) and not c.should_densify(550)
