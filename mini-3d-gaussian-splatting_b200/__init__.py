@@ -12,3 +12,4 @@ from . import losses, multiview, training  # noqa: F401,E402
 from .training import (ConfigManager, DensityController, GaussianOptimizer, GaussianTrainer, LearningRateScheduler, TrainingConfig,  # noqa: F401,E402
                        train_step)
 from .io_utils import CameraUtils, IOUtils  # noqa: F401,E402
+from .losses import GaussianLoss, SSIMLoss  # noqa: F401,E402

@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import pytest
 import torch
 
 import gsplat_b200 as gb
@@ -135,3 +136,37 @@ def test_camera_block_of_the_renderer_equals_the_oracles_camera():
         centre = -(wv[:3, :3].T @ wv[:3, 3])
         assert np.allclose(block[16:19], centre.numpy(), rtol=0, atol=1e-6)
         assert block[19] == 0.0
+
+
+def test_ssim_loss_equals_an_independent_statement_of_the_references_formula():
+    """src/core/loss.py:9-41 (which does not run) restated with scipy's 1-D correlation: same window, zero padding,
+    constants and clamp; D-SSIM is 0 for identical images, differentiable, and GaussianLoss mixes it as (1-l) L1 + l D-SSIM."""
+    import numpy as np
+    scipy_ndimage = pytest.importorskip("scipy.ndimage")
+    from importlib import import_module
+    losses = import_module("mini-3d-gaussian-splatting_b200.losses")
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(3, 40, 52, generator=g)
+    b = (a + 0.2 * torch.randn(3, 40, 52, generator=g)).clamp(0, 1)
+    K = 11
+    x = np.arange(K) - (K - 1) / 2
+    w = np.exp(-x ** 2 / (2 * (K / 6) ** 2)); w /= w.sum()
+
+    def blur(img):
+        out = scipy_ndimage.correlate1d(img, w, axis=2, mode="constant", cval=0.0)
+        return scipy_ndimage.correlate1d(out, w, axis=1, mode="constant", cval=0.0)
+
+    A, B = a.double().numpy(), b.double().numpy()
+    mx, my = blur(A), blur(B)
+    sx, sy, sxy = blur(A * A) - mx * mx, blur(B * B) - my * my, blur(A * B) - mx * my
+    ssim = ((2 * mx * my + 1e-4) * (2 * sxy + 9e-4)) / ((mx ** 2 + my ** 2 + 1e-4) * (sx + sy + 9e-4))
+    want = 1.0 - np.clip(ssim, 0, 1).mean()
+    loss = losses.SSIMLoss()
+    assert float(loss(a, b)) == pytest.approx(want, abs=2e-6)
+    assert float(loss(a.unsqueeze(0), b.unsqueeze(0))) == pytest.approx(want, abs=2e-6)
+    assert float(loss(a, a)) == pytest.approx(0.0, abs=1e-6)
+    pred = b.clone().requires_grad_(True)
+    total, parts = losses.GaussianLoss(0.2)(pred, a)
+    total.backward()
+    assert parts["total_loss"] == pytest.approx(0.8 * parts["l1"] + 0.2 * parts["dssim"], rel=1e-6)
+    assert parts["dssim"] == pytest.approx(want, abs=2e-6) and float(pred.grad.abs().max()) > 0
