@@ -13,3 +13,4 @@ from .training import (ConfigManager, DensityController, GaussianOptimizer, Gaus
                        train_step)
 from .io_utils import CameraUtils, IOUtils  # noqa: F401,E402
 from .losses import GaussianLoss, SSIMLoss  # noqa: F401,E402
+from .math_utils import MathUtils  # noqa: F401,E402

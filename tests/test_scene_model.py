@@ -27,7 +27,7 @@ def _rotation_from_wxyz(q: torch.Tensor) -> torch.Tensor:
 
 def _model(n: int, extent: float = 1.0) -> "gb.GaussianModel":
     m = gb.GaussianModel(device="cpu")
-    m.create_from_random(n, extent)
+    m.create_from_random(n, extent, seed=11)
     return m
 
 
@@ -95,3 +95,24 @@ def test_split_adds_one_net_point_per_large_splat_and_clone_one_per_small_splat(
     for p in (m._xyz, m._features_dc, m._features_rest, m._scaling, m._rotation, m._opacity):
         assert p.shape[0] == n1 + k and p.requires_grad
     assert m.xyz_gradient_accum.shape[0] == n1 + k and m.denom.shape[0] == n1 + k and m.max_radii2D.shape[0] == n1 + k
+
+
+def test_math_utils_carry_the_references_names_and_the_sh_rows_of_the_device_path():
+    """math_utils.py:7-49: rotation and covariance equal the model's own; degree 0 returns the DC row (the reference's
+    behaviour); degrees 1..3 equal DC + the oracle's basis (pinned to scipy in tests/test_oracle_golden.py) times the
+    higher-order rows."""
+    from oracle import splat_oracle as so
+    n = 50
+    m = _model(n)
+    with torch.no_grad():
+        m._scaling += 0.4 * torch.randn(n, 3, generator=torch.Generator().manual_seed(2))
+    assert torch.equal(gb.MathUtils.build_rotation_matrix(m._rotation), gb.scene.quaternion_to_rotation(m._rotation))
+    assert torch.allclose(gb.MathUtils.build_covariance_3d(m.get_scaling, m._rotation), m.compute_3d_covariance(), rtol=1e-5, atol=1e-9)
+    g = torch.Generator().manual_seed(4)
+    coeffs = torch.randn(n, 16, 3, generator=g, dtype=torch.float64)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g, dtype=torch.float64), dim=-1)
+    assert torch.equal(gb.MathUtils.spherical_harmonics_eval(0, dirs, coeffs), coeffs[:, 0])
+    for deg in (1, 2, 3):
+        Y = so.sh_basis(deg, dirs)
+        want = coeffs[:, 0] + (Y.unsqueeze(-1) * coeffs[:, 1:1 + Y.shape[1]]).sum(dim=1)
+        assert torch.allclose(gb.MathUtils.spherical_harmonics_eval(deg, dirs, coeffs), want, rtol=1e-12, atol=1e-12)
